@@ -1,0 +1,385 @@
+// capi.cu -- the C ABI of libb200fft.so (include/b200fft.h): library state,
+// plan construction (which kernel runs which axis) and plan execution.
+//
+// Plan layout mirrors what fftw_planxfftn builds for FFTW's guru interface
+// (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:10-77): the transformed axes
+// become one batched 1-D step each, everything else is batch.  Every step views
+// the C-contiguous block as (outer, n, inner) and runs either
+//   - the power-of-two Stockham kernel (c2c, n = 2^k <= 8192), contiguous
+//     (inner == 1) or strided flavour, or
+//   - the dense-matrix kernel (any kind, any n <= B2F_GENERIC_MAX_N).
+// The first step goes in -> out, the rest run in place on out (c2r: in place on
+// in, then in -> out), so a d-axis stage costs exactly one read and one write
+// of the block per axis and no scratch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "b200fft.h"
+#include "dft_generic.h"
+#include "internal.h"
+#include "fft_configs.h"
+
+#define B2F_GENERIC_MAX_N 4096
+
+namespace b2f {
+
+// ---- library state ---------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+static std::mutex g_mu;
+static std::map<std::string, int64_t> g_opts;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return B2F_ECUDA;
+}
+int64_t option(const char* key, int64_t dflt) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_opts.find(key);
+    if (it != g_opts.end()) return it->second;
+    std::string env = std::string("B2F_") + key;
+    for (auto& c : env) c = (char)toupper((unsigned char)c);
+    const char* v = getenv(env.c_str());
+    if (v && *v) return atoll(v);
+    return dflt;
+}
+
+// ---- caches ----------------------------------------------------------------
+struct DevKey {
+    int dev, a;
+    long long n;
+    bool operator<(const DevKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (a != o.a) return a < o.a;
+        return n < o.n;
+    }
+};
+static std::map<DevKey, void*> g_tw;
+struct MatEntry { double* d; int rows, cols; };
+static std::map<DevKey, MatEntry> g_mat;
+
+const void* twiddle_table(int n, int precision) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevKey key{dev, precision, n};
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) return it->second;
+    const long double TWO_PI = 6.28318530717958647692528676655900577L;
+    void* d = nullptr;
+    if (precision == 8) {
+        std::vector<double> h(2 * (size_t)n);
+        for (int k = 0; k < n; ++k) {
+            const long double a = TWO_PI * (long double)k / (long double)n;
+            h[2 * k] = (double)cosl(a);
+            h[2 * k + 1] = (double)(-sinl(a));
+        }
+        if (cudaMalloc(&d, h.size() * 8) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    } else {
+        std::vector<float> h(2 * (size_t)n);
+        for (int k = 0; k < n; ++k) {
+            const long double a = TWO_PI * (long double)k / (long double)n;
+            h[2 * k] = (float)cosl(a);
+            h[2 * k + 1] = (float)(-sinl(a));
+        }
+        if (cudaMalloc(&d, h.size() * 4) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    }
+    g_tw[key] = d;
+    return d;
+}
+
+const double* generic_matrix(int kind, long long n, int* rows, int* cols) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevKey key{dev, kind, n};
+    auto it = g_mat.find(key);
+    if (it != g_mat.end()) {
+        *rows = it->second.rows;
+        *cols = it->second.cols;
+        return it->second.d;
+    }
+    std::vector<double> M;
+    long long r = 0, c = 0;
+    if (build_matrix(kind, n, M, r, c) != 0) return nullptr;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, M.size() * 8) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, M.data(), M.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    g_mat[key] = MatEntry{d, (int)r, (int)c};
+    *rows = (int)r;
+    *cols = (int)c;
+    return d;
+}
+
+// ---- plan ------------------------------------------------------------------
+enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1 };
+enum Buf { BUF_IN = 0, BUF_OUT = 1 };
+
+struct Step {
+    StepType type;
+    int kind;
+    int axis;
+    long long outer, inner;
+    long long n_in, n_out;   // elements along the axis in source / destination
+    int in_c, out_c;         // reals per element
+    Buf src, dst;
+    // pow2
+    const void* tw;
+    bool swap;
+    // generic
+    const double* M;
+    int rows, cols;
+};
+
+static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+}  // namespace b2f
+
+using namespace b2f;
+
+struct b2f_plan_s {
+    int precision;
+    int ndims;
+    int kind0;
+    std::vector<long long> sizes_in, sizes_out;
+    std::vector<Step> steps;
+};
+
+static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long long>& shp_in,
+                    const std::vector<long long>& shp_out, int in_c, int out_c, Buf src, Buf dst) {
+    Step s;
+    memset(&s, 0, sizeof(s));
+    s.kind = kind;
+    s.axis = axis;
+    s.outer = 1;
+    s.inner = 1;
+    for (int i = 0; i < axis; ++i) s.outer *= shp_in[i];
+    for (int i = axis + 1; i < pl->ndims; ++i) s.inner *= shp_in[i];
+    s.n_in = shp_in[axis];
+    s.n_out = shp_out[axis];
+    s.in_c = in_c;
+    s.out_c = out_c;
+    s.src = src;
+    s.dst = dst;
+    // logical transform length: the real side for r2c / c2r
+    const long long n = (kind == B2F_C2R) ? s.n_out : s.n_in;
+    if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_pow2(n) && n <= B2F_POW2_MAX_N) {
+        s.type = STEP_POW2;
+        s.swap = (kind == B2F_BACKWARD);
+        s.tw = twiddle_table((int)n, pl->precision);
+        if (!s.tw) {
+            set_error("twiddle table allocation failed");
+            return B2F_ECUDA;
+        }
+    } else {
+        if (n > B2F_GENERIC_MAX_N) {
+            set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
+                      " is not supported by this build (power-of-two c2c up to 8192, any kind up to 4096)");
+            return B2F_EUNSUPPORTED;
+        }
+        s.type = STEP_GENERIC;
+        s.M = generic_matrix(kind, n, &s.rows, &s.cols);
+        if (!s.M) {
+            set_error("cannot build transform matrix (kind " + std::to_string(kind) + ", n " + std::to_string(n) + ")");
+            return B2F_EINVAL;
+        }
+        if (s.rows != s.n_out * out_c || s.cols != s.n_in * in_c) {
+            set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
+            return B2F_EINVAL;
+        }
+    }
+    pl->steps.push_back(s);
+    return B2F_OK;
+}
+
+extern "C" {
+
+int b2f_version(void) { return B2F_VERSION; }
+const char* b2f_last_error(void) { return g_err.c_str(); }
+int64_t b2f_launch_count(void) { return g_launches.load(); }
+
+int b2f_set_option(const char* key, int64_t value) {
+    if (!key) return B2F_EINVAL;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_opts[key] = value;
+    return B2F_OK;
+}
+int64_t b2f_get_option(const char* key) { return key ? option(key, 0) : 0; }
+
+int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int64_t* sizes_out,
+                  int naxes, const int* axes, const int* kind, int precision, unsigned flags) {
+    (void)flags;
+    if (!plan || !sizes_in || !sizes_out || !axes || !kind || ndims < 1 || naxes < 1 || naxes > ndims) {
+        set_error("b2f_planxfftn: bad arguments");
+        return B2F_EINVAL;
+    }
+    if (precision != 4 && precision != 8) {
+        set_error("precision must be 4 (float) or 8 (double); long double has no device type");
+        return B2F_EUNSUPPORTED;
+    }
+    std::vector<int> ax(axes, axes + naxes);
+    std::vector<char> seen(ndims, 0);
+    for (int i = 0; i < naxes; ++i) {
+        if (ax[i] < 0) ax[i] += ndims;
+        if (ax[i] < 0 || ax[i] >= ndims || seen[ax[i]]) {
+            set_error("b2f_planxfftn: bad or repeated axis");
+            return B2F_EINVAL;
+        }
+        seen[ax[i]] = 1;
+    }
+    b2f_plan_s* pl = new b2f_plan_s;
+    pl->precision = precision;
+    pl->ndims = ndims;
+    pl->kind0 = kind[0];
+    pl->sizes_in.assign(sizes_in, sizes_in + ndims);
+    pl->sizes_out.assign(sizes_out, sizes_out + ndims);
+    for (int i = 0; i < ndims; ++i)
+        if (sizes_in[i] < 1 || sizes_out[i] < 1) {
+            delete pl;
+            set_error("b2f_planxfftn: sizes must be positive");
+            return B2F_EINVAL;
+        }
+    const int k0 = kind[0];
+    const int last = ax[naxes - 1];
+    int rc = B2F_OK;
+    auto same_except = [&](int except) {
+        for (int i = 0; i < ndims; ++i)
+            if (i != except && sizes_in[i] != sizes_out[i]) return false;
+        return true;
+    };
+    if (k0 == B2F_FORWARD || k0 == B2F_BACKWARD) {
+        if (!same_except(-1)) rc = B2F_EINVAL;
+        for (int i = naxes - 1; i >= 0 && rc == B2F_OK; --i)
+            rc = add_step(pl, k0, ax[i], pl->sizes_in, pl->sizes_out, 2, 2,
+                          i == naxes - 1 ? BUF_IN : BUF_OUT, BUF_OUT);
+    } else if (k0 == B2F_R2C) {
+        if (!same_except(last) || sizes_out[last] != sizes_in[last] / 2 + 1) rc = B2F_EINVAL;
+        if (rc == B2F_OK) rc = add_step(pl, B2F_R2C, last, pl->sizes_in, pl->sizes_out, 1, 2, BUF_IN, BUF_OUT);
+        for (int i = naxes - 2; i >= 0 && rc == B2F_OK; --i)
+            rc = add_step(pl, B2F_FORWARD, ax[i], pl->sizes_out, pl->sizes_out, 2, 2, BUF_OUT, BUF_OUT);
+    } else if (k0 == B2F_C2R) {
+        if (!same_except(last) || sizes_in[last] != sizes_out[last] / 2 + 1) rc = B2F_EINVAL;
+        for (int i = 0; i < naxes - 1 && rc == B2F_OK; ++i)
+            rc = add_step(pl, B2F_BACKWARD, ax[i], pl->sizes_in, pl->sizes_in, 2, 2, BUF_IN, BUF_IN);
+        if (rc == B2F_OK) rc = add_step(pl, B2F_C2R, last, pl->sizes_in, pl->sizes_out, 2, 1, BUF_IN, BUF_OUT);
+    } else {
+        if (!same_except(-1)) rc = B2F_EINVAL;
+        for (int i = naxes - 1; i >= 0 && rc == B2F_OK; --i) {
+            if (kind[i] < B2F_REDFT00 || kind[i] > B2F_RODFT11) {
+                rc = B2F_EINVAL;
+                break;
+            }
+            rc = add_step(pl, kind[i], ax[i], pl->sizes_in, pl->sizes_out, 1, 1,
+                          i == naxes - 1 ? BUF_IN : BUF_OUT, BUF_OUT);
+        }
+    }
+    if (rc != B2F_OK) {
+        if (rc == B2F_EINVAL && g_err.empty()) set_error("b2f_planxfftn: sizes_in/sizes_out/kind are inconsistent");
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return B2F_OK;
+}
+
+int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* stream) {
+    if (!pl || !d_in || !d_out) {
+        set_error("b2f_execute: null plan or buffer");
+        return B2F_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int variant = (int)option("variant", 0);
+    const int variant_c = (int)option("variant_contig", variant);
+    const int variant_s = (int)option("variant_strided", variant);
+    const size_t nsteps = pl->steps.size();
+    for (size_t si = 0; si < nsteps; ++si) {
+        const Step& s = pl->steps[si];
+        const void* src = (s.src == BUF_IN) ? d_in : d_out;
+        void* dst = (s.dst == BUF_IN) ? const_cast<void*>(d_in) : d_out;
+        const double sc = (si + 1 == nsteps) ? scale : 1.0;
+        cudaError_t e;
+        if (s.type == STEP_POW2) {
+            FftParams prm;
+            memset(&prm, 0, sizeof(prm));
+            prm.in = src;
+            prm.out = dst;
+            prm.tw = s.tw;
+            prm.scale = sc;
+            prm.swap = s.swap ? 1 : 0;
+            const bool strided = s.inner > 1;
+            const int n = (int)s.n_in;
+            if (strided) {
+                prm.in_ostride = prm.out_ostride = s.n_in * s.inner;
+                prm.in_nstride = prm.out_nstride = s.inner;
+                prm.inner = s.inner;
+            } else {
+                prm.in_ostride = prm.out_ostride = s.n_in;
+                prm.npencils = s.outer;
+            }
+            int var = strided ? variant_s : variant_c;
+            auto launch = [&](int v) -> cudaError_t {
+                if (pl->precision == 8) {
+                    if (n <= 256) return launch_pow2_small_f64(n, v, strided, prm, s.outer, st);
+                    if (n <= 1024) return launch_pow2_mid_f64(n, v, strided, prm, s.outer, st);
+                    return launch_pow2_large_f64(n, v, strided, prm, s.outer, st);
+                }
+                if (n <= 256) return launch_pow2_small_f32(n, v, strided, prm, s.outer, st);
+                if (n <= 1024) return launch_pow2_mid_f32(n, v, strided, prm, s.outer, st);
+                return launch_pow2_large_f32(n, v, strided, prm, s.outer, st);
+            };
+            e = launch(var);
+            if (e == cudaErrorInvalidValue && var != 0) e = launch(0);   // variant not built for this n
+        } else {
+            GenericParams g;
+            memset(&g, 0, sizeof(g));
+            g.in = src;
+            g.out = dst;
+            g.M = s.M;
+            g.npencils = s.outer * s.inner;
+            g.inner = s.inner;
+            g.in_n = s.n_in;
+            g.out_n = s.n_out;
+            g.in_c = s.in_c;
+            g.out_c = s.out_c;
+            g.rows = s.rows;
+            g.cols = s.cols;
+            g.scale = sc;
+            e = launch_generic(pl->precision, g, st);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "b2f_execute: kernel launch");
+    }
+    return B2F_OK;
+}
+
+int b2f_destroy_plan(b2f_plan pl) {
+    delete pl;   // tables are cached library-wide
+    return B2F_OK;
+}
+
+int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
+    if (!pl || !buf || !buflen) return B2F_EINVAL;
+    std::string s;
+    for (const Step& st : pl->steps) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s kind=%d axis=%d n_in=%lld n_out=%lld outer=%lld inner=%lld %s->%s\n",
+                 st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig") : "dense-matrix",
+                 st.kind, st.axis, st.n_in, st.n_out, st.outer, st.inner,
+                 st.src == BUF_IN ? "in" : "out", st.dst == BUF_IN ? "in" : "out");
+        s += line;
+    }
+    strncpy(buf, s.c_str(), buflen - 1);
+    buf[buflen - 1] = 0;
+    return B2F_OK;
+}
+
+}  // extern "C"

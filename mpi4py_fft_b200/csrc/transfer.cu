@@ -1,0 +1,420 @@
+// transfer.cu -- the global transpose: pack kernel -> NCCL all-to-all(v) ->
+// unpack kernel, all enqueued on the caller's stream.
+//
+// Replaces MPI_Alltoallw over subarray datatypes
+// (/root/reference/mpi4py_fft/pencil.py:12-29 builds one datatype per peer that
+// selects block i of the balanced distribution along an axis; pencil.py:182-183
+// / 200-201 exchange them).  Equivalent formulation used here:
+//   forward : peer i is sent   A[.., sA_i:sA_i+nA_i (axisA), ..]   (C order)
+//             and its block lands in B[.., sB_i:sB_i+nB_i (axisB), ..]
+//   backward: the same with A and B swapped.
+// A block is contiguous in its array exactly when nothing but unit extents
+// precede the split axis (outer == 1); then the pack (or unpack) pass is skipped
+// and NCCL reads (writes) the array directly.
+//
+// NCCL is bound at run time with dlopen (the copy torch already loaded when
+// there is one), so the library has no link-time dependency on it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "b200fft.h"
+#include "internal.h"
+
+namespace b2f {
+
+// ---- NCCL binding ----------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    bool ok = false;
+    std::string why;
+};
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+
+static void load_nccl() {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy already in the process (torch's)
+        if (h) break;
+    }
+    if (!h) {
+        const char* env = getenv("B2F_NCCL_LIB");
+        if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    for (const char* n : names) {
+        if (h) break;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!h) {
+        g_nccl.why = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return;
+    }
+    g_nccl.handle = h;
+#define B2F_SYM(field, name)                                                  \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));  \
+    if (!g_nccl.field) {                                                      \
+        g_nccl.why = std::string("libnccl lacks symbol ") + name;             \
+        return;                                                               \
+    }
+    B2F_SYM(GetUniqueId, "ncclGetUniqueId")
+    B2F_SYM(CommInitRank, "ncclCommInitRank")
+    B2F_SYM(CommDestroy, "ncclCommDestroy")
+    B2F_SYM(Send, "ncclSend")
+    B2F_SYM(Recv, "ncclRecv")
+    B2F_SYM(GroupStart, "ncclGroupStart")
+    B2F_SYM(GroupEnd, "ncclGroupEnd")
+    B2F_SYM(GetErrorString, "ncclGetErrorString")
+    B2F_SYM(GetVersion, "ncclGetVersion")
+#undef B2F_SYM
+    g_nccl.ok = true;
+}
+
+static int need_nccl() {
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl.ok) {
+        set_error(g_nccl.why);
+        return B2F_ENCCL;
+    }
+    return B2F_OK;
+}
+static int nccl_fail(ncclResult_t r, const char* what) {
+    set_error(std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"));
+    return B2F_ENCCL;
+}
+
+// ---- balanced block distribution (== reference pencil.py:5-9) -----------------
+struct BlockDist {
+    long long n, p, q, r;   // n items over p owners: q = n / p, first r owners get q + 1
+    __host__ __device__ long long start(long long i) const { return i * q + (i < r ? i : r); }
+    __host__ __device__ long long len(long long i) const { return q + (i < r ? 1 : 0); }
+    __host__ __device__ long long owner(long long a) const {
+        const long long big = r * (q + 1);
+        return a < big ? a / (q + 1) : r + (a - big) / q;
+    }
+};
+static BlockDist make_dist(long long n, long long p) { return BlockDist{n, p, n / p, n % p}; }
+
+// ---- pack / unpack kernel -----------------------------------------------------
+// The array is (outer, N, U) in units of V bytes (U = inner * itemsize / V); the
+// packed buffer holds, for owner i = 0..p-1 in turn, the block
+// (outer, len(i), U) in C order, i.e. segment i starts at unit outer*U*start(i).
+// One thread moves one unit; consecutive threads walk a row of the array, so
+// both sides are accessed in contiguous runs of len(i)*U units.
+template <class V, bool PACK>
+__global__ void __launch_bounds__(256) copy_blocks_kernel(const V* __restrict__ src, V* __restrict__ dst,
+                                                         long long outer, long long U, BlockDist bd) {
+    const long long row = bd.n * U;
+    const long long total = outer * row;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+        const long long o = idx / row;
+        const long long u = idx - o * row;
+        const long long a = u / U;
+        const long long i = bd.owner(a);
+        const long long s = bd.start(i), ln = bd.len(i);
+        const long long packed = outer * U * s + o * ln * U + (u - s * U);
+        if (PACK) dst[packed] = src[idx];
+        else dst[idx] = src[packed];
+    }
+}
+
+template <bool PACK>
+static cudaError_t launch_copy_blocks(const void* src, void* dst, long long outer, long long n, long long inner,
+                                      int itemsize, long long p, cudaStream_t st) {
+    const long long row_bytes_per_a = inner * itemsize;
+    int v = 16;
+    while (v > 1 && (row_bytes_per_a % v || ((uintptr_t)src % v) || ((uintptr_t)dst % v))) v >>= 1;
+    const long long U = row_bytes_per_a / v;
+    const long long total = outer * n * U;
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    const long long cap = 148LL * 16;   // persistent-ish grid: 16 CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    const BlockDist bd = make_dist(n, p);
+    switch (v) {
+        case 16: copy_blocks_kernel<uint4, PACK><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)src, (uint4*)dst, outer, U, bd); break;
+        case 8: copy_blocks_kernel<uint2, PACK><<<(unsigned)blocks, 256, 0, st>>>((const uint2*)src, (uint2*)dst, outer, U, bd); break;
+        case 4: copy_blocks_kernel<uint32_t, PACK><<<(unsigned)blocks, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, outer, U, bd); break;
+        case 2: copy_blocks_kernel<uint16_t, PACK><<<(unsigned)blocks, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, outer, U, bd); break;
+        default: copy_blocks_kernel<uint8_t, PACK><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, outer, U, bd); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- workspace: two grow-only staging buffers per device ------------------------
+struct Workspace {
+    void* buf[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+};
+static Workspace g_ws[64];
+static std::mutex g_ws_mu;
+static int workspace(int slot, size_t bytes, void** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    Workspace& w = g_ws[dev & 63];
+    if (w.cap[slot] < bytes) {
+        if (w.buf[slot]) {
+            e = cudaFree(w.buf[slot]);   // synchronises: no transfer in flight can still use it
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFree(workspace)");
+            w.buf[slot] = nullptr;
+            w.cap[slot] = 0;
+        }
+        e = cudaMalloc(&w.buf[slot], bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(transfer workspace)");
+        w.cap[slot] = bytes;
+    }
+    *out = w.buf[slot];
+    return B2F_OK;
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+struct b2f_comm_s {
+    ncclComm_t comm;
+    int nranks, rank;
+};
+
+struct b2f_transfer_s {
+    b2f_comm comm;
+    int nranks, rank, ndims, itemsize;
+    std::vector<long long> shape, subA, subB;
+    int axisA, axisB;
+    long long outerA, innerA, NA, outerB, innerB, NB;
+    long long volA, volB;   // elements
+};
+
+extern "C" {
+
+int b2f_comm_unique_id(void* id128) {
+    if (!id128) return B2F_EINVAL;
+    int rc = need_nccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+    memcpy(id128, &id, 128);
+    return B2F_OK;
+}
+
+int b2f_comm_create(b2f_comm* comm, const void* id128, int nranks, int rank) {
+    if (!comm || !id128 || nranks < 1 || rank < 0 || rank >= nranks) {
+        set_error("b2f_comm_create: bad arguments");
+        return B2F_EINVAL;
+    }
+    int rc = need_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t c;
+    ncclResult_t r = g_nccl.CommInitRank(&c, nranks, id, rank);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitRank");
+    *comm = new b2f_comm_s{c, nranks, rank};
+    return B2F_OK;
+}
+
+int b2f_comm_destroy(b2f_comm comm) {
+    if (!comm) return B2F_OK;
+    if (g_nccl.ok && comm->comm) g_nccl.CommDestroy(comm->comm);
+    delete comm;
+    return B2F_OK;
+}
+
+int b2f_transfer_create(b2f_transfer* out, b2f_comm comm, int nranks, int rank, int ndims,
+                        const int64_t* shape, int itemsize, const int64_t* subshapeA, int axisA,
+                        const int64_t* subshapeB, int axisB) {
+    if (!out || !shape || !subshapeA || !subshapeB || ndims < 2 || nranks < 1 || rank < 0 || rank >= nranks ||
+        axisA < 0 || axisA >= ndims || axisB < 0 || axisB >= ndims || axisA == axisB || itemsize < 1) {
+        set_error("b2f_transfer_create: bad arguments");
+        return B2F_EINVAL;
+    }
+    // comm may be NULL: the handle then serves geometry / pack / unpack only
+    if (comm && (comm->nranks != nranks || comm->rank != rank)) {
+        set_error("b2f_transfer_create: communicator does not match nranks/rank");
+        return B2F_EINVAL;
+    }
+    b2f_transfer_s* t = new b2f_transfer_s;
+    t->comm = comm;
+    t->nranks = nranks;
+    t->rank = rank;
+    t->ndims = ndims;
+    t->itemsize = itemsize;
+    t->shape.assign(shape, shape + ndims);
+    t->subA.assign(subshapeA, subshapeA + ndims);
+    t->subB.assign(subshapeB, subshapeB + ndims);
+    t->axisA = axisA;
+    t->axisB = axisB;
+    // consistency with the balanced distribution: A is full along axisA and holds
+    // my block of axisB, B the other way round, every other extent is shared
+    const BlockDist dA = make_dist(shape[axisA], nranks), dB = make_dist(shape[axisB], nranks);
+    bool ok = shape[axisA] >= nranks && shape[axisB] >= nranks;
+    for (int i = 0; i < ndims && ok; ++i) {
+        if (i == axisA) ok = subshapeA[i] == shape[i] && subshapeB[i] == dA.len(rank);
+        else if (i == axisB) ok = subshapeB[i] == shape[i] && subshapeA[i] == dB.len(rank);
+        else ok = subshapeA[i] == shape[i] && subshapeB[i] == shape[i];
+    }
+    if (!ok) {
+        delete t;
+        set_error("b2f_transfer_create: subshapes are not the balanced blocks of shape for this rank");
+        return B2F_EINVAL;
+    }
+    auto prod = [](const std::vector<long long>& v, int a, int b) {
+        long long p = 1;
+        for (int i = a; i < b; ++i) p *= v[i];
+        return p;
+    };
+    t->NA = shape[axisA];
+    t->NB = shape[axisB];
+    t->outerA = prod(t->subA, 0, axisA);
+    t->innerA = prod(t->subA, axisA + 1, ndims);
+    t->outerB = prod(t->subB, 0, axisB);
+    t->innerB = prod(t->subB, axisB + 1, ndims);
+    t->volA = prod(t->subA, 0, ndims);
+    t->volB = prod(t->subB, 0, ndims);
+    *out = t;
+    return B2F_OK;
+}
+
+int b2f_transfer_destroy(b2f_transfer t) {
+    delete t;
+    return B2F_OK;
+}
+
+int b2f_transfer_geometry(b2f_transfer t, int64_t* send_counts, int64_t* send_offsets, int64_t* recv_counts,
+                          int64_t* recv_offsets) {
+    if (!t) return B2F_EINVAL;
+    const BlockDist dA = make_dist(t->NA, t->nranks), dB = make_dist(t->NB, t->nranks);
+    const long long rowA = t->outerA * t->innerA, rowB = t->outerB * t->innerB;
+    for (int i = 0; i < t->nranks; ++i) {
+        if (send_counts) send_counts[i] = dA.len(i) * rowA;
+        if (send_offsets) send_offsets[i] = dA.start(i) * rowA;
+        if (recv_counts) recv_counts[i] = dB.len(i) * rowB;
+        if (recv_offsets) recv_offsets[i] = dB.start(i) * rowB;
+    }
+    return B2F_OK;
+}
+
+// direction 0: pack A by axisA blocks; 1: pack B by axisB blocks
+int b2f_transfer_pack(b2f_transfer t, int direction, const void* d_src, void* d_packed, void* stream) {
+    if (!t || !d_src || !d_packed) return B2F_EINVAL;
+    cudaError_t e = direction == 0
+        ? launch_copy_blocks<true>(d_src, d_packed, t->outerA, t->NA, t->innerA, t->itemsize, t->nranks, (cudaStream_t)stream)
+        : launch_copy_blocks<true>(d_src, d_packed, t->outerB, t->NB, t->innerB, t->itemsize, t->nranks, (cudaStream_t)stream);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "pack kernel");
+}
+
+// direction 0: scatter packed segments into B by axisB blocks; 1: into A by axisA blocks
+int b2f_transfer_unpack(b2f_transfer t, int direction, const void* d_packed, void* d_dst, void* stream) {
+    if (!t || !d_packed || !d_dst) return B2F_EINVAL;
+    cudaError_t e = direction == 0
+        ? launch_copy_blocks<false>(d_packed, d_dst, t->outerB, t->NB, t->innerB, t->itemsize, t->nranks, (cudaStream_t)stream)
+        : launch_copy_blocks<false>(d_packed, d_dst, t->outerA, t->NA, t->innerA, t->itemsize, t->nranks, (cudaStream_t)stream);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "unpack kernel");
+}
+
+static int run_transfer(b2f_transfer t, int direction, const void* d_src, void* d_dst, cudaStream_t st) {
+    // geometry of the source side (S) and destination side (D) for this direction
+    const long long outerS = direction == 0 ? t->outerA : t->outerB;
+    const long long innerS = direction == 0 ? t->innerA : t->innerB;
+    const long long NS = direction == 0 ? t->NA : t->NB;
+    const long long outerD = direction == 0 ? t->outerB : t->outerA;
+    const long long innerD = direction == 0 ? t->innerB : t->innerA;
+    const long long ND = direction == 0 ? t->NB : t->NA;
+    const size_t bytesS = (size_t)(direction == 0 ? t->volA : t->volB) * t->itemsize;
+    const size_t bytesD = (size_t)(direction == 0 ? t->volB : t->volA) * t->itemsize;
+    const int p = t->nranks;
+    if (p == 1) {
+        // both pencils are the whole group-local block: plain copy
+        if (d_src != d_dst) {
+            cudaError_t e = cudaMemcpyAsync(d_dst, d_src, bytesS, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(transfer, single rank)");
+        }
+        return B2F_OK;
+    }
+    if (!t->comm) {
+        set_error("transfer was created without a communicator (geometry/pack-only handle)");
+        return B2F_EINVAL;
+    }
+    int rc = need_nccl();
+    if (rc) return rc;
+    const char* sendbase = (const char*)d_src;
+    char* recvbase = (char*)d_dst;
+    if (outerS != 1) {
+        void* ws;
+        if ((rc = workspace(0, bytesS, &ws))) return rc;
+        if ((rc = b2f_transfer_pack(t, direction, d_src, ws, st))) return rc;
+        sendbase = (const char*)ws;
+    }
+    if (outerD != 1) {
+        void* ws;
+        if ((rc = workspace(1, bytesD, &ws))) return rc;
+        recvbase = (char*)ws;
+    }
+    const BlockDist dS = make_dist(NS, p), dD = make_dist(ND, p);
+    const long long rowS = outerS * innerS * t->itemsize, rowD = outerD * innerD * t->itemsize;   // bytes per unit of the split axis
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+    for (int k = 0; k < p; ++k) {
+        // start with my right-hand neighbour so that the p ranks do not all hit peer 0 first
+        const int i = (t->rank + k) % p;
+        const size_t sbytes = (size_t)(dS.len(i) * rowS), soff = (size_t)(dS.start(i) * rowS);
+        const size_t rbytes = (size_t)(dD.len(i) * rowD), roff = (size_t)(dD.start(i) * rowD);
+        if (i == t->rank) {
+            cudaError_t e = cudaMemcpyAsync(recvbase + roff, sendbase + soff, sbytes, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) {
+                g_nccl.GroupEnd();
+                return cuda_fail(e, "cudaMemcpyAsync(self segment)");
+            }
+            continue;
+        }
+        r = g_nccl.Send(sendbase + soff, sbytes, ncclUint8, i, t->comm->comm, st);
+        if (r == ncclSuccess) r = g_nccl.Recv(recvbase + roff, rbytes, ncclUint8, i, t->comm->comm, st);
+        if (r != ncclSuccess) {
+            g_nccl.GroupEnd();
+            return nccl_fail(r, "ncclSend/ncclRecv");
+        }
+    }
+    r = g_nccl.GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+    if (outerD != 1) {
+        if ((rc = b2f_transfer_unpack(t, direction, recvbase, d_dst, st))) return rc;
+    }
+    return B2F_OK;
+}
+
+int b2f_transfer_forward(b2f_transfer t, const void* d_A, void* d_B, void* stream) {
+    if (!t || !d_A || !d_B) {
+        set_error("b2f_transfer_forward: null argument");
+        return B2F_EINVAL;
+    }
+    return run_transfer(t, 0, d_A, d_B, (cudaStream_t)stream);
+}
+
+int b2f_transfer_backward(b2f_transfer t, const void* d_B, void* d_A, void* stream) {
+    if (!t || !d_A || !d_B) {
+        set_error("b2f_transfer_backward: null argument");
+        return B2F_EINVAL;
+    }
+    return run_transfer(t, 1, d_B, d_A, (cudaStream_t)stream);
+}
+
+}  // extern "C"

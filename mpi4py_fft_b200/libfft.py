@@ -1,0 +1,190 @@
+"""Serial (one rank) transform stage: the backend plug point of the reference.
+
+Interface of /root/reference/mpi4py_fft/libfft.py (``FFT(shape, axes, dtype,
+padding, backend, transforms, **kw)`` with ``.forward`` / ``.backward`` callables
+exposing ``.input_array`` / ``.output_array``), backed by a single device
+planner instead of the reference's table of CPU backends (libfft.py:379-385).
+
+Differences that follow from living in HBM:
+  * arrays are allocated on first touch, planning is host arithmetic;
+  * ``forward(u)`` runs straight from ``u`` (and into ``output_array`` when one
+    is given) whenever those are device arrays of the planned shape -- the two
+    staging copies of libfft.py:213-216 disappear; host (numpy) arrays are
+    staged through the plan-owned device arrays;
+  * normalisation is a scale fused into the last kernel pass, not a second
+    sweep (libfft.py:412-413).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import fftw
+from .devarray import ArraySpec, DeviceArray, np_dtype_of
+
+
+def _Xfftn_plan_b200(shape, axes, dtype, transforms, options):
+    """(forward, backward) planned transform objects for one stage; same role
+    as ``_Xfftn_plan_fftw`` (reference libfft.py:48-79)."""
+    options = dict(options)
+    threads = options.pop('threads', 1)
+    effort = options.pop('planner_effort', 'FFTW_MEASURE')
+    options.pop('overwrite_input', None)
+    flags = (fftw.flag_dict.get(effort, 0),)
+
+    transforms = {} if transforms is None else transforms
+    if tuple(axes) in transforms:
+        plan_fwd, plan_bck = transforms[tuple(axes)]
+    elif np.issubdtype(dtype, np.floating):
+        plan_fwd, plan_bck = fftw.rfftn, fftw.irfftn
+    else:
+        plan_fwd, plan_bck = fftw.fftn, fftw.ifftn
+
+    s = tuple(int(n) for n in np.take(shape, axes))
+    U = ArraySpec(shape, dtype)
+    fwd = plan_fwd(U, s=s, axes=axes, threads=threads, flags=flags)
+    V = fwd._out
+    bck = plan_bck(V, s=s, axes=axes, threads=threads, flags=flags, output_array=U)
+    return fwd, bck
+
+
+class _Stage(object):
+    """One direction of a serial stage as a callable with arrays attached."""
+
+    def __init__(self, owner, planned, default_normalize):
+        self._owner = owner
+        self._planned = planned
+        self._default_normalize = default_normalize
+
+    @property
+    def input_array(self):
+        return self._owner._array(self._planned, 'in')
+
+    @property
+    def output_array(self):
+        return self._owner._array(self._planned, 'out')
+
+    @property
+    def input_shape(self):
+        return self._planned.input_shape
+
+    @property
+    def output_shape(self):
+        return self._planned.output_shape
+
+    @property
+    def input_dtype(self):
+        return self._planned.input_dtype
+
+    @property
+    def output_dtype(self):
+        return self._planned.output_dtype
+
+    @property
+    def destroys_input(self):
+        """multi-axis complex-to-real overwrites what it reads (as FFTW's c2r)"""
+        return self._planned.kind == fftw.C2R and len(self._planned.axes) > 1
+
+    def run(self, src, dst, normalize=None):
+        """Device arrays in, device arrays out, no staging (used by PFFT)."""
+        if normalize is None:
+            normalize = self._default_normalize
+        self._planned.execute(src, dst, self._owner.M if normalize else 1.0)
+        return dst
+
+    def __call__(self, input_array=None, output_array=None, **kw):
+        normalize = kw.pop('normalize', self._default_normalize)
+        src = self._planned._usable(input_array, self.input_shape, self.input_dtype)
+        if src is not None and self.destroys_input and src is not self.input_array:
+            src = None      # stage through the owned array: the caller's input must survive
+        if src is None:
+            src = self.input_array
+            if input_array is not None:
+                src[...] = input_array
+        dst = self._planned._usable(output_array, self.output_shape, self.output_dtype)
+        direct = dst is not None
+        if dst is None:
+            dst = self.output_array
+        self.run(src, dst, normalize)
+        if output_array is not None and not direct:
+            output_array[...] = np.asarray(dst) if isinstance(output_array, np.ndarray) else dst
+            return output_array
+        return dst
+
+
+class FFTBase(object):
+    """Argument normalisation shared by serial transforms (reference
+    libfft.py:221-261)."""
+
+    def __init__(self, shape, axes=None, dtype=float, padding=False):
+        shape = [int(n) for n in shape] if np.ndim(shape) else [int(shape)]
+        assert len(shape) > 0
+        assert min(shape) > 0
+        if axes is None:
+            axes = list(range(len(shape)))
+        else:
+            axes = [int(a) for a in axes] if np.ndim(axes) else [int(axes)]
+            axes = [a + len(shape) if a < 0 else a for a in axes]
+        assert min(axes) >= 0
+        assert max(axes) < len(shape)
+        assert 0 < len(axes) <= len(shape)
+        assert sorted(axes) == sorted(set(axes))
+        dtype = np.dtype(dtype)
+        assert dtype.char in 'fdgFDG'
+        self.shape = shape
+        self.axes = axes
+        self.dtype = dtype
+        self.padding = padding
+        self.real_transform = np.issubdtype(dtype, np.floating)
+        self.padding_factor = 1
+
+
+class FFT(FFTBase):
+    """Serial transform over ``axes`` of a block of ``shape`` on the device.
+
+    ``forward`` is normalised by default and ``backward`` is not;
+    ``normalize=`` at call time overrides either (reference libfft.py:408-422).
+    ``backend`` is accepted for source compatibility; every value runs the
+    B200 kernels (there are no CPU backends in this package).
+    """
+
+    def __init__(self, shape, axes=None, dtype=float, padding=False, backend='b200',
+                 transforms=None, **kw):
+        FFTBase.__init__(self, shape, axes, dtype, padding)
+        if self.dtype.char in 'gG':
+            raise RuntimeError("long double transforms are not available on the device")
+        pf = 1.0
+        if padding is not False:
+            pf = padding[self.axes[-1]] if np.ndim(padding) else padding
+        if abs(pf - 1.0) > 1e-8:
+            raise NotImplementedError("padded (dealiased) transforms are not part of this build yet")
+        self.padding_factor = 1.0
+        self.backend = backend
+        self.fwd, self.bck = _Xfftn_plan_b200(self.shape, self.axes, self.dtype, transforms, kw)
+        self.M = self.fwd.get_normalization()
+        # the two plan-owned arrays: physical side U, spectral side V
+        self._U = None
+        self._V = None
+        self.forward = _Stage(self, self.fwd, True)
+        self.backward = _Stage(self, self.bck, False)
+
+    def _array(self, planned, side):
+        physical = (planned is self.fwd) == (side == 'in')
+        if physical:
+            if self._U is None:
+                self._U = ArraySpec(self.fwd.input_shape, self.fwd.input_dtype).allocate()
+            return self._U
+        if self._V is None:
+            self._V = ArraySpec(self.fwd.output_shape, self.fwd.output_dtype).allocate()
+        return self._V
+
+    def adopt(self, U=None, V=None):
+        """Let the stage use caller-provided device arrays as its owned pair
+        (PFFT shares one pair of work arrays between stages)."""
+        if U is not None:
+            self._U = U
+        if V is not None:
+            self._V = V
+
+    def destroy(self):
+        self.fwd.destroy()
+        self.bck.destroy()

@@ -1,0 +1,392 @@
+"""Parallel multidimensional transforms: ``PFFT`` on B200.
+
+Same constructor, attributes and call semantics as the reference's ``PFFT`` /
+``Transform`` (/root/reference/mpi4py_fft/mpifft.py:8-79,202-419): a chain of
+serial stages (one or more undivided axes each) separated by global
+redistributions, forward normalised, backward not.  What changes is where the
+data lives and how it moves:
+
+  * every array is device resident; stages are ``b2f_execute`` launches and
+    redistributions are ``b2f_transfer_*`` (pack -> NCCL all-to-all -> unpack),
+    all enqueued on the current CUDA stream -- a whole forward or backward is
+    one stream with no host round trip;
+  * the reference allocates an input and an output array per stage and copies
+    between them (mpifft.py:66,76; libfft.py:72-78).  Here the chain is mapped
+    onto at most two work buffers plus the two end-point arrays: c2c/r2r stages
+    run in place, a redistribution inside a group of one rank is an alias (no
+    bytes move), the first stage reads the caller's array directly and the last
+    stage writes the caller's output directly.  See ``Transform._layout``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .devarray import ArraySpec, DeviceArray, as_tensor, np_dtype_of, torch_dtype, device
+from .libfft import FFT
+from .pencil import Pencil, Subcomm
+
+
+class _Buffers(object):
+    """End-point arrays X (physical) / Y (spectral) and two byte work buffers,
+    shared by the forward and backward transforms of one PFFT; all lazy."""
+
+    def __init__(self, x_spec, y_spec):
+        self.spec = {'X': x_spec, 'Y': y_spec}
+        self.arr = {}
+        self.work = {}
+
+    def endpoint(self, name):
+        if name not in self.arr:
+            self.arr[name] = self.spec[name].allocate(fill=0)
+        return self.arr[name]
+
+    def view(self, name, shape, dtype):
+        """Typed view of work buffer ``name`` (grown on demand)."""
+        import torch
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        buf = self.work.get(name)
+        if buf is None or buf.numel() < nbytes:
+            self.work[name] = None
+            buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device())
+            self.work[name] = buf
+        return DeviceArray(buf[:nbytes].view(torch_dtype(dtype)).view(tuple(shape)))
+
+
+class Transform(object):
+    """One direction of a parallel transform (forward or backward).
+
+    ``xfftn`` are the per-stage callables, ``transfer`` the redistributions
+    between them (bound methods of :class:`Transfer`), ``pencil`` the input and
+    output pencils; as in the reference ``len(xfftn) == len(transfer) + 1``.
+    """
+
+    def __init__(self, xfftn, transfer, pencil, buffers=None, ends=('X', 'Y')):
+        assert len(xfftn) == len(transfer) + 1 and len(pencil) == 2
+        self._xfftn = tuple(xfftn)
+        self._transfer = tuple(transfer)
+        self._pencil = tuple(pencil)
+        if buffers is None:
+            buffers = _Buffers(ArraySpec(xfftn[0].input_shape, xfftn[0].input_dtype),
+                               ArraySpec(xfftn[-1].output_shape, xfftn[-1].output_dtype))
+            ends = ('X', 'Y')
+        self._buffers = buffers
+        self._ends = ends
+        self._plan = self._layout()
+
+    # -- arrays -------------------------------------------------------------------
+    @property
+    def input_array(self):
+        return self._buffers.endpoint(self._ends[0])
+
+    @property
+    def output_array(self):
+        return self._buffers.endpoint(self._ends[1])
+
+    @property
+    def input_pencil(self):
+        return self._pencil[0]
+
+    @property
+    def output_pencil(self):
+        return self._pencil[1]
+
+    # -- static buffer assignment ---------------------------------------------------
+    def _layout(self):
+        """Where every intermediate of the chain lives.
+
+        Logical arrays: a_i (input of stage i), b_i (its output), with
+        a_{i+1} = T_i(b_i).  Labels: 'IN' (the caller's / end-point input, never
+        written), 'OUT' (the final destination), 'W0'/'W1' (work buffers).
+          * a_{i+1} shares b_i's buffer when T_i acts inside a group of one;
+          * b_i shares a_i's buffer when the stage can run in place;
+          * 'OUT' is propagated backwards from the last stage as far as those
+            two rules allow, so the tail of the chain needs no extra copy.
+        """
+        m = len(self._xfftn)
+        inplace = []
+        for st in self._xfftn:
+            inplace.append(st.input_shape == st.output_shape and st.input_dtype == st.output_dtype)
+        trivial = [getattr(t, '__self__', t).comm.Get_size() == 1 for t in self._transfer]
+        a = [None] * m
+        b = [None] * m
+        a[0] = 'IN'
+        b[m - 1] = 'OUT'
+        i = m - 1
+        while i > 0 and inplace[i]:
+            a[i] = 'OUT'
+            if not trivial[i - 1]:
+                break
+            b[i - 1] = 'OUT'
+            i -= 1
+        toggle = 0
+        for i in range(m):
+            if i > 0 and a[i] is None:
+                if trivial[i - 1]:
+                    a[i] = b[i - 1]
+                else:
+                    toggle ^= 1
+                    a[i] = 'W%d' % toggle
+            if b[i] is None:
+                if inplace[i] and a[i] not in ('IN',):
+                    b[i] = a[i]
+                else:
+                    toggle ^= 1
+                    b[i] = 'W%d' % toggle
+                    if b[i] == a[i]:   # cannot happen with two buffers, but stay safe
+                        toggle ^= 1
+                        b[i] = 'W%d' % toggle
+        return dict(a=a, b=b, trivial=trivial)
+
+    # -- execution -------------------------------------------------------------------
+    def _resolve(self, label, shape, dtype, src, out):
+        if label == 'IN':
+            return src
+        if label == 'OUT':
+            return out
+        return self._buffers.view(label, shape, dtype)
+
+    def __call__(self, input_array=None, output_array=None, **kw):
+        """Compute the transform.
+
+        ``input_array`` / ``output_array`` may be device arrays of the planned
+        shape and dtype (used directly), host arrays (staged through the
+        plan-owned end-point arrays) or omitted (the end-point arrays are used
+        and the output end point is returned, as in the reference).
+        ``normalize=True/False`` is forwarded to every stage.
+        """
+        first, last = self._xfftn[0], self._xfftn[-1]
+        src = _usable(input_array, first.input_shape, first.input_dtype)
+        if src is None:
+            src = self.input_array
+            if input_array is not None:
+                src[...] = input_array
+        out = _usable(output_array, last.output_shape, last.output_dtype)
+        direct_out = out is not None
+        if out is None:
+            out = self.output_array
+
+        plan = self._plan
+        m = len(self._xfftn)
+        if getattr(first, 'destroys_input', False) and plan['a'][0] == 'IN' and input_array is not None \
+                and src is not self.input_array:
+            # a multi-axis c2r stage overwrites what it reads: keep the caller's array intact
+            self.input_array[...] = src
+            src = self.input_array
+        cur = src
+        for i in range(m):
+            st = self._xfftn[i]
+            dst = self._resolve(plan['b'][i], st.output_shape, st.output_dtype, src, out)
+            st.run(cur, dst, kw.get('normalize'))
+            if i + 1 < m:
+                if plan['trivial'][i]:
+                    cur = dst
+                else:
+                    nxt = self._xfftn[i + 1]
+                    recv = self._resolve(plan['a'][i + 1], nxt.input_shape, nxt.input_dtype, src, out)
+                    self._transfer[i](dst, recv)
+                    cur = recv
+
+        if output_array is not None and not direct_out:
+            if isinstance(output_array, np.ndarray):
+                output_array[...] = np.asarray(out)
+            else:
+                output_array[...] = out
+            return output_array
+        return out
+
+
+def _usable(a, shape, dtype):
+    """``a`` as a device array that a kernel can read/write directly, or None."""
+    if a is None or isinstance(a, np.ndarray):
+        return None
+    try:
+        t = as_tensor(a)
+    except TypeError:
+        return None
+    if tuple(t.shape) != tuple(shape) or np_dtype_of(a) != np.dtype(dtype):
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        return None
+    return a
+
+
+class PFFT(object):
+    """Parallel FFT (and r2r) over a block-distributed array on B200 GPUs.
+
+    Parameters are the reference's (mpifft.py:82-204): ``comm`` (a communicator
+    of this package, a :class:`Subcomm`, or a Cartesian communicator), ``shape``,
+    ``axes`` (None | int | sequence of ints | sequence of sequences),
+    ``dtype``, ``grid``, ``padding`` (must be False in this build), ``collapse``,
+    ``backend`` (ignored: device kernels), ``transforms`` (axes tuple ->
+    (forward planner, backward planner) from :mod:`mpi4py_fft_b200.fftw`),
+    ``darray``, ``slab`` (deprecated).
+
+    ``forward(input_array=None, output_array=None, **kw)`` and ``backward(...)``
+    are :class:`Transform` instances.
+    """
+
+    def __init__(self, comm, shape=None, axes=None, dtype=float, grid=None, padding=False,
+                 collapse=False, backend='b200', transforms=None, darray=None, **kw):
+        if shape is None:
+            assert darray is not None
+            shape = darray.pencil.shape
+        ndim = len(shape)
+
+        # -- axes -> list of groups (tuples), one serial stage per group
+        if axes is None:
+            axes = list(range(ndim))
+            if darray is not None:
+                # the aligned axis of darray must be transformed first (= listed last)
+                axes = list(np.roll(axes, ndim - 1 - darray.alignment))
+        elif isinstance(axes, (int, np.integer)):
+            axes = [axes]
+        else:
+            axes = list(axes)
+        groups = []
+        for ax in axes:
+            if isinstance(ax, (int, np.integer)):
+                grp = [int(ax) % ndim] if -ndim <= ax < ndim else [int(ax)]
+            else:
+                assert isinstance(ax, (tuple, list))
+                grp = []
+                for a in ax:
+                    assert isinstance(a, (int, np.integer))
+                    grp.append(int(a) + ndim if a < 0 else int(a))
+            assert min(grp) >= 0
+            assert max(grp) < ndim
+            assert 0 < len(grp) <= ndim
+            assert sorted(grp) == sorted(set(grp))
+            groups.append(tuple(grp))
+        self.axes = groups
+        shape = [int(n) for n in shape]
+
+        if darray is None:
+            dtype = np.dtype(dtype)
+            assert dtype.char in 'fdgFDG'
+            if padding is not False:
+                raise NotImplementedError("padded (dealiased) PFFT is not part of this build yet")
+            self._input_shape = tuple(shape)
+            assert len(shape) > 0
+            assert min(shape) > 0
+            slab = kw.pop('slab', False)
+
+            if grid is not None:
+                assert not isinstance(comm, Subcomm)
+                assert slab is False
+                grid = tuple(grid)
+                assert len(grid) <= ndim
+                comm = Subcomm(comm, list(grid) + [1] * (ndim - len(grid)))
+
+            if isinstance(comm, Subcomm):
+                assert slab is False
+                assert len(comm) == ndim
+                assert all(comm[ax].Get_size() == 1 for ax in groups[-1])
+                self.subcomm = comm
+            else:
+                if slab is False or slab is None:
+                    dims = [0] * ndim
+                    for ax in groups[-1]:
+                        dims[ax] = 1
+                else:  # deprecated slab keyword
+                    if slab is True:
+                        axis = (groups[-1][-1] + 1) % ndim
+                    else:
+                        axis = int(slab) % ndim
+                    dims = [1] * ndim
+                    dims[axis] = comm.Get_size()
+                self.subcomm = Subcomm(comm, dims)
+        else:
+            dtype = darray.dtype
+            self.subcomm = darray.subcomm
+            self._input_shape = tuple(shape)
+            sizes = darray.commsizes
+            assert all(sizes[ax] == 1 for ax in groups[-1]), \
+                "Set keyword axes such that axes to transform first are aligned"
+
+        self.collapse = collapse
+        if collapse is True:
+            # merge, from the back, every group whose axes are all undivided into
+            # the stage that runs first; divided groups stay separate stages
+            merged = [[]]
+            for grp in reversed(groups):
+                if all(self.subcomm[a].Get_size() == 1 for a in grp):
+                    merged[0] = list(grp) + merged[0]
+                else:
+                    merged.insert(0, list(grp))
+            groups = merged
+
+        self.axes = tuple(tuple(g) for g in groups)
+        self.xfftn = []
+        self.transfer = []
+        self.pencil = [None, None]
+
+        # -- first stage: the axes that are undivided on input
+        grp = self.axes[-1]
+        pencil = Pencil(self.subcomm, shape, grp[-1])
+        stage = FFT(pencil.subshape, grp, dtype, padding, backend=backend, transforms=transforms, **kw)
+        self.xfftn.append(stage)
+        self.pencil[0] = pencilA = pencil
+        if shape[grp[-1]] != stage.forward.output_shape[grp[-1]]:
+            # real-to-complex: global shape shrinks along that axis, dtype is promoted
+            dtype = stage.forward.output_dtype
+            shape[grp[-1]] = stage.forward.output_shape[grp[-1]]
+            pencilA = Pencil(self.subcomm, shape, grp[-1])
+
+        # -- remaining stages, each behind a redistribution
+        for grp in reversed(self.axes[:-1]):
+            pencilB = pencilA.pencil(grp[-1])
+            self.transfer.append(pencilA.transfer(pencilB, dtype))
+            stage = FFT(pencilB.subshape, grp, dtype, padding, backend=backend, transforms=transforms, **kw)
+            self.xfftn.append(stage)
+            pencilA = pencilB
+            if shape[grp[-1]] != stage.forward.output_shape[grp[-1]]:
+                dtype = stage.forward.output_dtype
+                shape[grp[-1]] = stage.forward.output_shape[grp[-1]]
+                pencilA = Pencil(pencilB.subcomm, shape, grp[-1])
+
+        self.pencil[1] = pencilA
+        self._output_shape = tuple(shape)
+
+        first, last = self.xfftn[0], self.xfftn[-1]
+        self._buffers = _Buffers(ArraySpec(first.forward.input_shape, first.forward.input_dtype),
+                                 ArraySpec(last.forward.output_shape, last.forward.output_dtype))
+        self.forward = Transform([s.forward for s in self.xfftn],
+                                 [t.forward for t in self.transfer],
+                                 self.pencil, self._buffers, ('X', 'Y'))
+        self.backward = Transform([s.backward for s in self.xfftn[::-1]],
+                                  [t.backward for t in self.transfer[::-1]],
+                                  self.pencil[::-1], self._buffers, ('Y', 'X'))
+
+    def destroy(self):
+        if isinstance(self.subcomm, Subcomm):
+            self.subcomm.destroy()
+        for t in self.transfer:
+            t.destroy()
+        for s in self.xfftn:
+            s.destroy()
+
+    def shape(self, forward_output=True):
+        """Local shape: spectral space if ``forward_output`` else physical."""
+        if forward_output is not True:
+            return self.forward.input_pencil.subshape
+        return tuple(self.xfftn[-1].forward.output_shape)
+
+    def local_slice(self, forward_output=True):
+        """Slices of the global array held by this rank."""
+        p = self.backward.input_pencil if forward_output is True else self.forward.input_pencil
+        return tuple(slice(s, s + n) for s, n in zip(p.substart, p.subshape))
+
+    def global_shape(self, forward_output=False):
+        """Global shape in spectral (``forward_output``) or physical space."""
+        return self._output_shape if forward_output else self._input_shape
+
+    @property
+    def dimensions(self):
+        return len(self.xfftn[0].forward.input_shape)
+
+    def dtype(self, forward_output=False):
+        """dtype of the spectral (``forward_output``) or physical arrays."""
+        if forward_output:
+            return self.xfftn[-1].forward.output_dtype
+        return self.xfftn[0].forward.input_dtype
