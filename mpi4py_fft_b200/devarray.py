@@ -90,6 +90,14 @@ class ArraySpec(object):
         return empty(self.shape, self.dtype, fill=fill)
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array (numpy view of pinned torch memory) for fast
+    staging in and out of device arrays."""
+    import torch
+    shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+    return torch.empty(shape, dtype=torch_dtype(dtype), pin_memory=True).numpy()
+
+
 def empty(shape, dtype=np.float64, fill=None):
     import torch
     shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
@@ -171,6 +179,15 @@ class DeviceArray(object):
         """device -> host copy as a plain ``numpy.ndarray``"""
         return self.__array__()
 
+    def copy_to_host(self, host):
+        """device -> host copy straight into ``host`` (numpy array of the same
+        shape and dtype; pinned memory gives full PCIe rate)"""
+        import torch
+        assert isinstance(host, np.ndarray) and host.dtype == self.dtype and tuple(host.shape) == self.shape
+        assert host.flags.c_contiguous
+        torch.from_numpy(host).copy_(self._t)
+        return host
+
     def set(self, host):
         """host -> device copy (``host`` broadcastable to ``self.shape``)"""
         self[...] = host
@@ -190,6 +207,10 @@ class DeviceArray(object):
         if isinstance(value, DeviceArray):
             value = value._t
         elif isinstance(value, np.ndarray):
+            dst = self._t[idx]
+            if value.dtype == self.dtype and tuple(value.shape) == tuple(dst.shape) and value.flags.c_contiguous:
+                dst.copy_(torch.from_numpy(value))       # one host->device copy, no staging tensor
+                return
             value = torch.from_numpy(np.ascontiguousarray(value)).to(self._t.device, non_blocking=False)
         elif not isinstance(value, (Number, torch.Tensor)):
             value = torch.as_tensor(np.asarray(value)).to(self._t.device)
@@ -263,3 +284,14 @@ def _unwrap_index(idx):
     if isinstance(idx, np.integer):
         return int(idx)
     return idx
+
+
+def copy_out(dev, target):
+    """``target[...] = dev`` for a host (numpy) or device target"""
+    if isinstance(target, np.ndarray):
+        if target.dtype == dev.dtype and tuple(target.shape) == dev.shape and target.flags.c_contiguous:
+            dev.copy_to_host(target)
+        else:
+            target[...] = np.asarray(dev)
+    else:
+        target[...] = dev

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..devarray import ArraySpec, DeviceArray, as_tensor, device_ptr, empty, np_dtype_of
+from ..devarray import copy_out as _copy_out, ArraySpec, DeviceArray, as_tensor, device_ptr, empty, np_dtype_of
 from .utilities import (FFTW_FORWARD, FFTW_BACKWARD, FFTW_REDFT00, FFTW_REDFT01, FFTW_REDFT10,
                         FFTW_REDFT11, FFTW_RODFT00, FFTW_RODFT01, FFTW_RODFT10, FFTW_RODFT11,
                         FFTW_MEASURE, FFTW_DESTROY_INPUT, FFTW_UNALIGNED, FFTW_CONSERVE_MEMORY,
@@ -150,7 +150,7 @@ class FFT(object):
             dst = self.output_array
         self.execute(src, dst, self._M if normalize else 1.0)
         if output_array is not None and not direct:
-            output_array[...] = np.asarray(dst) if isinstance(output_array, np.ndarray) else dst
+            _copy_out(dst, output_array)
             return output_array
         return dst
 

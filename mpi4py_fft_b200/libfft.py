@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import fftw
-from .devarray import ArraySpec, DeviceArray, np_dtype_of
+from .devarray import copy_out as _copy_out, ArraySpec, DeviceArray, np_dtype_of
 
 
 def _Xfftn_plan_b200(shape, axes, dtype, transforms, options):
@@ -106,7 +106,7 @@ class _Stage(object):
             dst = self.output_array
         self.run(src, dst, normalize)
         if output_array is not None and not direct:
-            output_array[...] = np.asarray(dst) if isinstance(output_array, np.ndarray) else dst
+            _copy_out(dst, output_array)
             return output_array
         return dst
 

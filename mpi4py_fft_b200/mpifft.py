@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .devarray import ArraySpec, DeviceArray, as_tensor, np_dtype_of, torch_dtype, device
+from .devarray import copy_out as _copy_out, ArraySpec, DeviceArray, as_tensor, np_dtype_of, torch_dtype, device
 from .libfft import FFT
 from .pencil import Pencil, Subcomm
 
@@ -188,10 +188,7 @@ class Transform(object):
                     cur = recv
 
         if output_array is not None and not direct_out:
-            if isinstance(output_array, np.ndarray):
-                output_array[...] = np.asarray(out)
-            else:
-                output_array[...] = out
+            _copy_out(out, output_array)
             return output_array
         return out
 

@@ -1,0 +1,344 @@
+"""PFFT / DistArray / Transfer on the device against the oracle and the
+reference's fixtures.
+
+  * one rank: the product end to end (PFFT.forward/backward through the C ABI);
+  * several ranks on ONE GPU: every rank of a golden multi-rank case is played
+    in turn -- the product's own plans, stage kernels and pack/unpack kernels
+    run on the device, only the wire (NCCL) is replaced by device copies of the
+    packed segments.  Results are compared with the gathered output of the
+    unmodified reference (tests/golden/values.npz);
+  * full-size properties at BASELINE config C2 (512^3 complex128): spot values
+    against a direct DFT, round trip, linearity, Parseval.
+"""
+from itertools import product
+
+import numpy as np
+import pytest
+
+import pfft_oracle as O
+from conftest import case_kwargs
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'d': 1e-12, 'f': 1e-5}
+
+
+def relerr(a, ref):
+    return np.abs(np.asarray(a) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def rand(shape, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    dtype = np.dtype(dtype)
+    x = rng.random(shape)
+    if dtype.char in 'FD':
+        x = x + 1j * rng.random(shape)
+    return x.astype(dtype)
+
+
+@pytest.fixture(scope='module')
+def B():
+    import torch
+    import mpi4py_fft_b200 as B
+    torch.cuda.set_device(0)
+    return B
+
+
+# ---------------------------------------------------------------------------
+# one rank
+# ---------------------------------------------------------------------------
+def test_single_rank_matches_reference_fixture(B, layouts, values):
+    """golden case c2c_32_p1 has no stored values (size); use the 2-rank input of
+    c1 on one rank: the global result must not depend on the decomposition"""
+    g = values['c1_c2c_16_p2__input']
+    fft = B.PFFT(B.COMM_WORLD, g.shape, dtype='D')
+    u = B.newDistArray(fft, False)
+    u[...] = g
+    uh = fft.forward(u)
+    assert relerr(uh, values['c1_c2c_16_p2__forward']) < 1e-12
+    ub = fft.backward(uh)
+    assert relerr(ub, g) < 1e-12
+    assert np.array_equal(np.asarray(u), g)          # caller's input preserved
+
+
+@pytest.mark.parametrize('dt', ['f', 'd', 'F', 'D'])
+def test_single_rank_matrix(B, dt):
+    """the reference's PFFT test matrix (tests/test_mpifft.py:53-177) on one rank:
+    dims 2-4, sizes (12, 13) plus powers of two, axes variants, collapse; values
+    against the transform of the global array and round trip"""
+    tol = TOL[dt.lower()]
+    axes_by_dim = {2: [None, (-1,), (-2,), (-1, -2), (-2, -1), (-1, 0), (0, -1), ((0,), (1,))],
+                   3: [None, ((0,), (1, 2)), ((0,), (-2, -1))],
+                   4: [None, ((0,), (1,), (2,), (3,)), ((0,), (1, 2, 3)), ((0,), (1,), (2, 3))]}
+    for dim in (2, 3, 4):
+        sizes = (12, 13) if dim < 4 else (6, 5)
+        shapes = list(product(*([sizes] * dim))) + [(16,) * dim, (8, 32, 4, 2)[:dim]]
+        if dim == 4:
+            shapes = shapes[::5]
+        for shape in shapes:
+            for collapse in (False, True):
+                for axes in axes_by_dim[dim]:
+                    fft = B.PFFT(B.COMM_WORLD, shape, axes=axes, dtype=dt, collapse=collapse)
+                    g = rand(shape, dt, 11)
+                    u = B.newDistArray(fft, False)
+                    u[...] = g
+                    uh = fft.forward(u)
+                    g64 = g.astype('D' if dt in 'FD' else 'd')
+                    ref = O.expected_forward(g64, axes)
+                    assert tuple(uh.shape) == ref.shape == fft.global_shape(True)
+                    assert relerr(uh, ref) < tol, (shape, axes, collapse, dt)
+                    ub = B.newDistArray(fft, False)
+                    ub = fft.backward(uh, ub)
+                    assert relerr(ub, g64) < 10 * tol, (shape, axes, collapse, dt)
+                    # implicit arrays (tests/test_mpifft.py:173-176)
+                    fft.forward.input_array[...] = g
+                    fft.forward()
+                    fft.backward()
+                    assert relerr(fft.backward.output_array, g64) < 10 * tol
+                    fft.destroy()
+
+
+def test_single_rank_r2r(B):
+    """tests/test_mpifft.py:35-51: DCT-III on (1,2), DST-III on (3,4), Fourier on 0"""
+    import functools
+    fftw = B.fftw
+    N = (5, 6, 7, 8, 9)
+    tr = {(1, 2): (functools.partial(fftw.dctn, type=3), functools.partial(fftw.idctn, type=3)),
+          (3, 4): (functools.partial(fftw.dstn, type=3), functools.partial(fftw.idstn, type=3))}
+    fft = B.PFFT(B.COMM_WORLD, N, axes=((0,), (1, 2), (3, 4)), grid=(-1,), transforms=tr)
+    g = rand(N, 'd', 3)
+    A = B.newDistArray(fft, False)
+    A[...] = g
+    Bh = fft.forward(A)
+    ref = O.expected_forward(g, ((0,), (1, 2), (3, 4)), {(1, 2): ('dct', 3), (3, 4): ('dst', 3)})
+    assert relerr(Bh, ref) < 1e-12
+    C = fft.backward(Bh)
+    assert relerr(C, g) < 1e-12
+
+
+def test_distarray_basics(B):
+    """tests/test_darray.py of the reference, one rank"""
+    from mpi4py_fft_b200 import DistArray, newDistArray, PFFT
+    z = DistArray((8, 6, 4), dtype=float, val=2.0)
+    assert z.global_shape == (8, 6, 4) and z.alignment == 2 and z.rank == 0 and z.dimensions == 3
+    assert z.local_slice() == (slice(0, 8), slice(0, 6), slice(0, 4))
+    assert float(np.asarray(z).sum()) == 2.0 * 8 * 6 * 4
+    v = DistArray((3, 8, 6, 4), rank=1, val=1.0)
+    assert v.pencil.shape == (8, 6, 4) and v.rank == 1
+    assert isinstance(v[0], DistArray) and v[0].rank == 0 and v[0].shape == (8, 6, 4)
+    assert not isinstance(v[0, 1], DistArray)
+    w = v * 2.0 + v
+    assert isinstance(w, DistArray) and float(np.asarray(w).max()) == 3.0
+    fft = PFFT(B.COMM_WORLD, darray=z)
+    assert fft.axes == ((0,), (1,), (2,))
+    z1 = z.redistribute(0)
+    assert z1 is z and z1.alignment == 0
+    u = newDistArray(fft, False, rank=1)
+    assert u.shape == (3, 8, 6, 4)
+    with pytest.raises(NotImplementedError):
+        z.write('x.h5')
+
+
+# ---------------------------------------------------------------------------
+# all ranks of a multi-rank case on one device
+# ---------------------------------------------------------------------------
+class Played(object):
+    """The product's PFFT for every rank of a job (planned under virtual_world),
+    executed stage by stage; a transfer packs on every rank, moves the packed
+    segments the way the all-to-all would, and unpacks on every rank."""
+
+    def __init__(self, B, nranks, kw):
+        from mpi4py_fft_b200.comm import virtual_world
+        from mpi4py_fft_b200._lib import TransferHandle
+        self.B, self.n = B, nranks
+        self.ffts, self.handles = [], []
+        for r in range(nranks):
+            with virtual_world(nranks, r):
+                f = B.PFFT(B.COMM_WORLD, **kw)
+                self.ffts.append(f)
+                self.handles.append([TransferHandle(t.comm, t.shape, t.dtype.itemsize, t.subshapeA, t.axisA,
+                                                    t.subshapeB, t.axisB, exchange=False) for t in f.transfer])
+
+    def _exchange(self, ti, arrays, backward):
+        import torch
+        B, n = self.B, self.n
+        trs = [f.transfer[ti] for f in self.ffts]
+        direction = 1 if backward else 0
+        packed, geos = [], []
+        for r in range(n):
+            t = trs[r]
+            src = arrays[r]
+            buf = B.fftw.aligned(src.shape, dtype=src.dtype)
+            self.handles[r][ti].pack(direction, src, buf)
+            packed.append(buf.tensor.reshape(-1))
+            geos.append(t.geometry)
+        out = []
+        for r in range(n):
+            t = trs[r]
+            group = t.comm.ranks
+            me = t.comm.Get_rank()
+            shape = t.subshapeA if backward else t.subshapeB
+            recv = torch.empty(int(np.prod(shape)), dtype=packed[r].dtype, device=packed[r].device)
+            rc = geos[r]['send_counts' if backward else 'recv_counts']
+            ro = geos[r]['send_offsets' if backward else 'recv_offsets']
+            for j, peer in enumerate(group):
+                sc = geos[peer]['recv_counts' if backward else 'send_counts']
+                so = geos[peer]['recv_offsets' if backward else 'send_offsets']
+                assert sc[me] == rc[j]
+                recv[ro[j]:ro[j] + rc[j]] = packed[peer][so[me]:so[me] + sc[me]]
+            dst = B.fftw.aligned(shape, dtype=arrays[r].dtype)
+            self.handles[r][ti].unpack(direction, B.DeviceArray(recv), dst)
+            out.append(dst)
+        return out
+
+    def forward(self, blocks):
+        B = self.B
+        cur = []
+        for r, f in enumerate(self.ffts):
+            a = B.fftw.aligned(blocks[r].shape, dtype=blocks[r].dtype)
+            a[...] = blocks[r]
+            cur.append(a)
+        nst = len(self.ffts[0].xfftn)
+        for i in range(nst):
+            nxt = []
+            for r, f in enumerate(self.ffts):
+                st = f.xfftn[i].forward
+                dst = B.fftw.aligned(st.output_shape, dtype=st.output_dtype)
+                st.run(cur[r], dst)
+                nxt.append(dst)
+            cur = nxt
+            if i + 1 < nst:
+                cur = self._exchange(i, cur, backward=False)
+        return cur
+
+    def backward(self, blocks):
+        B = self.B
+        cur = list(blocks)
+        nst = len(self.ffts[0].xfftn)
+        for i in range(nst - 1, -1, -1):
+            nxt = []
+            for r, f in enumerate(self.ffts):
+                st = f.xfftn[i].backward
+                dst = B.fftw.aligned(st.output_shape, dtype=st.output_dtype)
+                st.run(cur[r], dst)
+                nxt.append(dst)
+            cur = nxt
+            if i > 0:
+                cur = self._exchange(i - 1, cur, backward=True)
+        return cur
+
+
+MULTI = ['c1_c2c_16_p2', 'c3_c2c_16_p8_pencil', 'c4_r2c_16_p8_slab', 'c4_r2c_16_p8_slab_collapse',
+         'c5_c2c_8x4_p8_grid42', 'uneven_r2c_12_13_14_p4', 'uneven_c2c_13_12_11_p6_axes201',
+         'uneven_c2c_7_9_p3_2d', 'c2c_4d_nested_p4', 'r2c_3d_nested_collapse_p4']
+
+
+@pytest.mark.parametrize('name', MULTI)
+def test_all_ranks_played_on_one_gpu(B, layouts, values, name):
+    case = layouts[name]
+    n = case['meta']['nranks']
+    kw = case_kwargs(case['meta'])
+    g = values[name + '__input']
+    tol = TOL[g.dtype.char.lower()]
+    job = Played(B, n, kw)
+    ranks = case['ranks']
+    blocks = [np.ascontiguousarray(g[tuple(slice(a, b) for a, b in ranks[r]['local_slice_in'])]) for r in range(n)]
+    out = job.forward(blocks)
+    ref = values[name + '__forward']
+    for r in range(n):
+        sl = tuple(slice(a, b) for a, b in ranks[r]['local_slice_out'])
+        assert tuple(out[r].shape) == tuple(ranks[r]['local_shape_out'])
+        assert np.abs(np.asarray(out[r]) - ref[sl]).max() <= tol * max(1.0, np.abs(ref).max()), (name, r)
+    back = job.backward(out)
+    for r in range(n):
+        assert np.abs(np.asarray(back[r]) - blocks[r]).max() <= 10 * tol, (name, r)
+
+
+@pytest.mark.parametrize('itemsize_dtype', ['f', 'd', 'F', 'D'])
+def test_pack_unpack_kernels_vs_numpy(B, itemsize_dtype):
+    """pack == concatenation of the axis blocks in C order (what the reference's
+    subarray datatypes describe, pencil.py:12-29), unpack is its inverse; odd
+    extents exercise the 4/8/16-byte paths"""
+    from mpi4py_fft_b200.comm import virtual_world
+    from mpi4py_fft_b200._lib import TransferHandle
+    from mpi4py_fft_b200.pencil import _blockdist
+    dt = np.dtype(itemsize_dtype)
+    for shape, axisA, axisB, p in (((6, 7, 5), 2, 1, 3), ((9, 4, 3), 1, 0, 2), ((5, 8, 3, 7), 3, 1, 4), ((10, 6), 1, 0, 4)):
+        for rank in range(p):
+            nB, sB = _blockdist(shape[axisB], p, rank)
+            nA, sA = _blockdist(shape[axisA], p, rank)
+            subA = list(shape)
+            subA[axisB] = nB
+            subB = list(shape)
+            subB[axisA] = nA
+
+            class FakeComm(object):
+                ranks = tuple(range(p))
+
+                def Get_size(self):
+                    return p
+
+                def Get_rank(self):
+                    return rank
+            h = TransferHandle(FakeComm(), shape, dt.itemsize, subA, axisA, subB, axisB, exchange=False)
+            for direction, sub, axis in ((0, subA, axisA), (1, subB, axisB)):
+                x = rand(sub, dt, 4)
+                src = B.fftw.aligned(sub, dtype=dt)
+                src[...] = x
+                packed = B.fftw.aligned(sub, dtype=dt)
+                h.pack(direction, src, packed)
+                expect = np.concatenate([np.ascontiguousarray(
+                    np.take(x, range(_blockdist(shape[axis], p, i)[1], sum(_blockdist(shape[axis], p, i))), axis=axis)).ravel()
+                    for i in range(p)])
+                assert np.array_equal(np.asarray(packed).ravel(), expect), (shape, axis, direction)
+                # unpack of the other direction scatters back into the same layout
+                dst = B.fftw.aligned(sub, dtype=dt, fill=0)
+                h.unpack(1 - direction, packed, dst)
+                assert np.array_equal(np.asarray(dst), x)
+            h.destroy()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE config C2 at full size: properties that do not need a full oracle run
+# ---------------------------------------------------------------------------
+def _direct_dft_point(g, k):
+    """one output point of the normalised 3-D DFT by three tensor contractions"""
+    n0, n1, n2 = g.shape
+    w0 = np.exp(-2j * np.pi * k[0] * np.arange(n0) / n0)
+    w1 = np.exp(-2j * np.pi * k[1] * np.arange(n1) / n1)
+    w2 = np.exp(-2j * np.pi * k[2] * np.arange(n2) / n2)
+    return np.einsum('i,j,k,ijk->', w0, w1, w2, g, optimize=True) / g.size
+
+
+def test_full_size_c2_properties(B):
+    import torch
+    N = 512
+    shape = (N, N, N)
+    fft = B.PFFT(B.COMM_WORLD, shape, dtype='D')
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(0)
+    u = B.newDistArray(fft, False)
+    u.tensor.copy_(torch.view_as_complex(torch.rand(shape + (2,), dtype=torch.float64, device='cuda', generator=gen)))
+    uh = fft.forward(u)
+    # (1) spot values against a direct evaluation of the definition (oracle, host)
+    g = np.asarray(u)
+    for k in [(0, 0, 0), (1, 2, 3), (511, 0, 256), (37, 400, 129)]:
+        got = complex(uh.tensor[k].item())
+        assert abs(got - _direct_dft_point(g, k)) < 1e-12, k
+    # (2) Parseval: sum |u|^2 / N^3 == sum |u_hat|^2  (forward is normalised)
+    e_phys = float((u.tensor.abs() ** 2).sum().item()) / g.size
+    e_spec = float((uh.tensor.abs() ** 2).sum().item())
+    assert abs(e_phys - e_spec) < 1e-10 * e_phys
+    # (3) round trip
+    back = B.newDistArray(fft, False)
+    fft.backward(uh, back)
+    assert float((back.tensor - u.tensor).abs().max().item()) < 1e-12
+    # (4) linearity: F(a u + b v) == a F(u) + b F(v)
+    v = B.newDistArray(fft, False)
+    v.tensor.copy_(torch.view_as_complex(torch.rand(shape + (2,), dtype=torch.float64, device='cuda', generator=gen)))
+    uh_copy = uh.tensor.clone()
+    vh = fft.forward(v).tensor.clone()
+    w = B.newDistArray(fft, False)
+    w.tensor.copy_(2.5 * u.tensor - 0.5j * v.tensor)
+    wh = fft.forward(w)
+    assert float((wh.tensor - (2.5 * uh_copy - 0.5j * vh)).abs().max().item()) < 1e-12

@@ -1,0 +1,240 @@
+"""Serial transforms on the device (through the C ABI: b2f_planxfftn /
+b2f_execute) against the oracle -- numpy/scipy pocketfft and the plain-C
+restatement oracle/dft_ref.c.  Mirrors the reference's serial tests
+(tests/test_fftw.py:32-138, tests/test_libfft.py:23-135): all planners, dims
+1-3, every axis, f/d precision, r2r kinds 1-4, round trips -- plus exact value
+checks and the power-of-two sizes the Stockham kernels serve.
+
+Tolerances (north_star): 1e-12 (fp64) / 1e-5 (fp32) on transform values,
+relative to max|reference| for unnormalised results.
+"""
+import functools
+from itertools import product
+
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+import pfft_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'d': 1e-12, 'f': 1e-5}
+
+
+def relerr(a, ref):
+    return np.abs(np.asarray(a) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def rand(shape, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    dtype = np.dtype(dtype)
+    x = rng.random(shape)
+    if dtype.char in 'FD':
+        x = x + 1j * rng.random(shape)
+    return x.astype(dtype)
+
+
+@pytest.fixture(scope='module')
+def B():
+    import torch
+    import mpi4py_fft_b200 as B
+    torch.cuda.set_device(0)
+    return B
+
+
+def test_docstring_vectors_on_device(B):
+    """/root/reference/mpi4py_fft/fftw/xfftn.py:85-88,155-158,220-223,293-301,381-384"""
+    fftw = B.fftw
+    A = fftw.aligned(4, dtype='D')
+    plan = fftw.fftn(A)
+    A[:] = np.array([1, 2, 3, 4], dtype='D')
+    assert np.allclose(np.asarray(plan()), [10, -2 + 2j, -2, -2 - 2j], atol=1e-14)
+    assert plan.input_array is A and plan.output_array is plan()
+    iplan = fftw.ifftn(A)
+    assert np.allclose(np.asarray(iplan()), [10, -2 - 2j, -2, -2 + 2j], atol=1e-14)
+    R = fftw.aligned(4, dtype='d')
+    rplan = fftw.rfftn(R)
+    R[:] = np.array([1., 2, 3, 4])
+    assert np.allclose(np.asarray(rplan()), [10, -2 + 2j, -2], atol=1e-14)
+    c2r = fftw.irfftn(A)
+    assert np.allclose(np.asarray(c2r()), [15., -4., 0., -1., 0., -4.], atol=1e-13)
+    c2r7 = fftw.irfftn(A, s=(7,))
+    assert np.allclose(np.asarray(c2r7()), [19., -5.04891734, -0.30797853, -0.64310413, -0.64310413,
+                                            -0.30797853, -5.04891734])
+    dct = fftw.dctn(R)
+    assert np.allclose(np.asarray(dct()), [20., -6.30864406, 0., -0.44834153])
+    assert np.isclose(dct.get_normalization(), 1.0 / 8)
+
+
+@pytest.mark.parametrize('n', [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize('dt', ['D', 'F'])
+def test_stockham_pow2_c2c(B, n, dt):
+    """contiguous axis, strided axes with ragged tiles, forward/backward, fused
+    normalisation, in place -- every variant of fft_configs.h"""
+    from mpi4py_fft_b200 import _lib
+    tol = TOL[dt.lower()]
+    shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 2048 else [(2, n), (n, 5)]
+    try:
+        for variant in range(3):
+            _lib.set_option('variant', variant)
+            for shape in shapes:
+                axis = shape.index(n)
+                x = rand(shape, dt, seed=n + axis)
+                U = B.fftw.aligned(shape, dtype=dt)
+                U[...] = x
+                fwd = B.fftw.fftn(U, axes=(axis,))
+                y = fwd(normalize=True)
+                ref = np.fft.fft(x.astype('D'), axis=axis) / n
+                assert relerr(y, ref) < tol, ('fwd', n, dt, variant, shape)
+                assert 'stockham' in fwd.plan().describe()
+                bck = B.fftw.ifftn(fwd.output_array, axes=(axis,), output_array=U)
+                z = bck()
+                assert relerr(z, x.astype('D')) < tol, ('bwd', n, dt, variant, shape)
+                # in place
+                V = B.fftw.aligned(shape, dtype=dt)
+                V[...] = x
+                B.fftw.fftn(V, axes=(axis,), output_array=V)()
+                assert relerr(V, ref * n) < tol, ('inplace', n, dt, variant, shape)
+    finally:
+        _lib.set_option('variant', 0)
+
+
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_all_planners_small_sizes(B, dt):
+    """the reference's own matrix: dims 1-3, sizes (7, 8, 10), every axes
+    combination (tests/test_fftw.py:36-103) -- values against numpy, and the
+    r2c->c2r / c2c round trips the reference checks"""
+    fftw = B.fftw
+    tol = TOL[dt]
+    for dim in (1, 2, 3):
+        for shape in product(*([(7, 8, 10)] * dim)):
+            if dim == 3 and shape[0] != 7:
+                continue
+            allaxes = tuple(reversed(range(dim)))
+            for i in range(dim):
+                axes = tuple(reversed(allaxes[:i + 1]))
+                # r2c -> c2r
+                x = rand(shape, dt, 1)
+                A = fftw.aligned(shape, dtype=dt)
+                A[...] = x
+                r2c = fftw.rfftn(A, axes=axes)
+                Bh = r2c()
+                ref = np.fft.rfftn(x.astype('d'), axes=axes)
+                assert relerr(Bh, ref) < tol, ('r2c', shape, axes)
+                c2r = fftw.irfftn(r2c.output_array, s=np.take(shape, axes), axes=axes, output_array=A)
+                back = c2r(normalize=True)
+                assert relerr(back, x.astype('d')) < 10 * tol, ('c2r', shape, axes)
+                # c2c
+                z = rand(shape, dt.upper(), 2)
+                C = fftw.aligned(shape, dtype=dt.upper())
+                C[...] = z
+                c2c = fftw.fftn(C, axes=axes)
+                D = c2c()
+                assert relerr(D, np.fft.fftn(z.astype('D'), axes=axes)) < tol, ('c2c', shape, axes)
+                ic2c = fftw.ifftn(c2c.output_array, axes=axes, output_array=C)
+                assert relerr(ic2c(normalize=True), z.astype('D')) < 10 * tol
+
+
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_r2r_all_kinds(B, dt, dft_ref):
+    """DCT/DST types 1-4 against scipy (as tests/test_fftw.py:106-138) and
+    against the C restatement of FFTW's definitions; mixed kinds per axis"""
+    fftw = B.fftw
+    tol = 10 * TOL[dt]
+    for n in (5, 8, 13):
+        x = rand((n,), dt, n)
+        A = fftw.aligned((n,), dtype=dt)
+        for typ in (1, 2, 3, 4):
+            for fam, planner, iplanner in (('dct', fftw.dctn, fftw.idctn), ('dst', fftw.dstn, fftw.idstn)):
+                A[...] = x
+                p = planner(A, type=typ)
+                y = np.asarray(p())
+                assert relerr(y, getattr(sfft, fam)(x.astype('d'), type=typ)) < tol, (fam, typ, n)
+                kind = (fftw.dct_type if fam == 'dct' else fftw.dst_type)[typ]
+                assert relerr(y, dft_ref(kind, n, x.astype('d'))) < tol
+                ip = iplanner(p.output_array, type=typ, output_array=A)
+                assert relerr(ip(normalize=True), x.astype('d')) < tol, ('inv', fam, typ, n)
+    # several axes, a different kind on each (tests/test_fftw.py:119-133)
+    shape = (6, 7, 5)
+    x = rand(shape, dt, 3)
+    kinds = [fftw.FFTW_REDFT10, fftw.FFTW_RODFT01, fftw.FFTW_REDFT00]
+    A = fftw.aligned(shape, dtype=dt)
+    A[...] = x
+    out = fftw.aligned(shape, dtype=dt)
+    plan = fftw.FFT(A, out, axes=(0, 1, 2), kind=kinds, normalization=fftw.get_normalization(kinds, shape, (0, 1, 2)))
+    y = plan()
+    ref = O.serial_transform(x.astype('d'), (0, 1, 2), kinds)
+    assert relerr(y, ref) < tol
+    inv = fftw.FFT(out, A, axes=(0, 1, 2), kind=[fftw.inverse[k] for k in kinds],
+                   normalization=plan.get_normalization())
+    assert relerr(inv(normalize=True), x.astype('d')) < tol
+
+
+@pytest.mark.parametrize('n', [3, 5, 6, 7, 9, 12, 13, 24, 100])
+def test_generic_lengths_c2c(B, n, dft_ref):
+    """non powers of two (the reference's tests use 5..13) on every axis"""
+    for shape, axis in (((4, n), 1), ((n, 6), 0), ((3, n, 5), 1)):
+        z = rand(shape, 'D', n)
+        U = B.fftw.aligned(shape, dtype='D')
+        U[...] = z
+        p = B.fftw.fftn(U, axes=(axis,))
+        y = np.asarray(p())
+        assert relerr(y, np.fft.fft(z, axis=axis)) < 1e-12
+        assert 'dense-matrix' in p.plan().describe()
+    z = rand((n,), 'D', 1)
+    U = B.fftw.aligned((n,), dtype='D')
+    U[...] = z
+    assert relerr(B.fftw.fftn(U)(), dft_ref(-1, n, z)) < 1e-12
+
+
+@pytest.mark.parametrize('backendless', [True])
+def test_libfft_class(B, backendless):
+    """libfft.FFT as in the reference's tests/test_libfft.py: forward normalised,
+    backward not, round trip; given arrays are used directly"""
+    from mpi4py_fft_b200.libfft import FFT
+    for dt in 'fFdD':
+        tol = TOL[dt.lower()]
+        for dim in (1, 2, 3):
+            for shape in product(*([(7, 8, 9)] * dim)):
+                if dim == 3 and shape[1] != 8:
+                    continue
+                for axes in [None, (dim - 1,), tuple(range(dim))]:
+                    fft = FFT(shape, axes, dtype=dt)
+                    x = rand(shape, dt, 5)
+                    A = fft.forward.input_array
+                    A[...] = x
+                    Bh = fft.forward()
+                    ax = tuple(range(dim)) if axes is None else axes
+                    x64 = x.astype(dt.upper() if dt in 'FD' else 'd').astype('D' if dt in 'FD' else 'd')
+                    ref = (np.fft.fftn(x64, axes=ax) if dt in 'FD' else np.fft.rfftn(x64, axes=ax)) / np.prod(np.take(shape, ax))
+                    assert relerr(Bh, ref) < tol, (dt, shape, axes)
+                    C = fft.backward()
+                    assert relerr(C, x64) < 10 * tol
+                    # explicit arrays: used in place of the owned ones
+                    A2 = B.fftw.aligned_like(A)
+                    A2[...] = x
+                    out = B.fftw.aligned_like(Bh)
+                    r = fft.forward(A2, out)
+                    assert r is out and relerr(out, ref) < tol
+                    assert np.array_equal(np.asarray(A2), x)       # input preserved
+                    # host arrays are staged
+                    h = np.zeros(Bh.shape, dtype=Bh.dtype)
+                    fft.forward(x, h)
+                    assert relerr(h, ref) < tol
+                    # normalize flags swapped (tests/test_mpifft.py:246-251 idea)
+                    un = fft.forward(A2, normalize=False)
+                    assert relerr(np.asarray(un) / np.prod(np.take(shape, ax)), ref) < tol
+                    fft.destroy()
+
+
+def test_errors(B):
+    from mpi4py_fft_b200._lib import B200FFTError
+    with pytest.raises((B200FFTError, RuntimeError)):
+        U = B.fftw.aligned((3, 5000), dtype='D')     # non-pow2 beyond the dense-matrix limit
+        B.fftw.fftn(U, axes=(1,))()
+    with pytest.raises(NotImplementedError):
+        B.fftw.hfftn(None)
+    with pytest.raises(AssertionError):
+        U = B.fftw.aligned((4, 4), dtype='d')
+        B.fftw.fftn(U)
