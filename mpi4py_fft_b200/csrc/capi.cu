@@ -52,6 +52,39 @@ int64_t option(const char* key, int64_t dflt) {
     return dflt;
 }
 
+// ---- device facts -----------------------------------------------------------
+int sm_count() {
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cache[dev & 63];
+    if (!c) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        c = v;
+    }
+    return c;
+}
+
+typedef void* (*AnyFn)();
+void* driver_entry_point(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return q == cudaDriverEntryPointSuccess ? fn : nullptr;
+}
+
+}  // namespace b2f
+#include <cuda.h>
+namespace b2f {
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = (TensorMapEncodeFn)driver_entry_point("cuTensorMapEncodeTiled");
+    return fn;
+}
+
 // ---- caches ----------------------------------------------------------------
 struct DevKey {
     int dev, a;
@@ -62,41 +95,8 @@ struct DevKey {
         return n < o.n;
     }
 };
-static std::map<DevKey, void*> g_tw;
 struct MatEntry { double* d; int rows, cols; };
 static std::map<DevKey, MatEntry> g_mat;
-
-const void* twiddle_table(int n, int precision) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lk(g_mu);
-    DevKey key{dev, precision, n};
-    auto it = g_tw.find(key);
-    if (it != g_tw.end()) return it->second;
-    const long double TWO_PI = 6.28318530717958647692528676655900577L;
-    void* d = nullptr;
-    if (precision == 8) {
-        std::vector<double> h(2 * (size_t)n);
-        for (int k = 0; k < n; ++k) {
-            const long double a = TWO_PI * (long double)k / (long double)n;
-            h[2 * k] = (double)cosl(a);
-            h[2 * k + 1] = (double)(-sinl(a));
-        }
-        if (cudaMalloc(&d, h.size() * 8) != cudaSuccess) return nullptr;
-        if (cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-    } else {
-        std::vector<float> h(2 * (size_t)n);
-        for (int k = 0; k < n; ++k) {
-            const long double a = TWO_PI * (long double)k / (long double)n;
-            h[2 * k] = (float)cosl(a);
-            h[2 * k + 1] = (float)(-sinl(a));
-        }
-        if (cudaMalloc(&d, h.size() * 4) != cudaSuccess) return nullptr;
-        if (cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-    }
-    g_tw[key] = d;
-    return d;
-}
 
 const double* generic_matrix(int kind, long long n, int* rows, int* cols) {
     int dev = 0;
@@ -133,8 +133,7 @@ struct Step {
     long long n_in, n_out;   // elements along the axis in source / destination
     int in_c, out_c;         // reals per element
     Buf src, dst;
-    // pow2
-    const void* tw;
+    // pow2 (twiddle tables belong to the kernel instance, fft_pow2_inst.cuh)
     bool swap;
     // generic
     const double* M;
@@ -176,11 +175,6 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_pow2(n) && n <= B2F_POW2_MAX_N) {
         s.type = STEP_POW2;
         s.swap = (kind == B2F_BACKWARD);
-        s.tw = twiddle_table((int)n, pl->precision);
-        if (!s.tw) {
-            set_error("twiddle table allocation failed");
-            return B2F_ECUDA;
-        }
     } else {
         if (n > B2F_GENERIC_MAX_N) {
             set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
@@ -301,6 +295,9 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
     const int variant = (int)option("variant", 0);
     const int variant_c = (int)option("variant_contig", variant);
     const int variant_s = (int)option("variant_strided", variant);
+    const int variant_t = (int)option("variant_tma", 0);
+    const int engine = (int)option("strided_engine", 1);
+    const bool strict = option("variant_strict", 0) != 0;
     const size_t nsteps = pl->steps.size();
     for (size_t si = 0; si < nsteps; ++si) {
         const Step& s = pl->steps[si];
@@ -313,7 +310,6 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
             memset(&prm, 0, sizeof(prm));
             prm.in = src;
             prm.out = dst;
-            prm.tw = s.tw;
             prm.scale = sc;
             prm.swap = s.swap ? 1 : 0;
             const bool strided = s.inner > 1;
@@ -337,8 +333,22 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
                 if (n <= 1024) return launch_pow2_mid_f32(n, v, strided, prm, s.outer, st);
                 return launch_pow2_large_f32(n, v, strided, prm, s.outer, st);
             };
-            e = launch(var);
-            if (e == cudaErrorInvalidValue && var != 0) e = launch(0);   // variant not built for this n
+            // strided axes: TMA-staged persistent kernel where one is built for n and
+            // the layout can be described to TMA, else the register-path kernel
+            //   strided_engine: 0 = auto, 1 = register path only, 2 = TMA only (sweeps)
+            e = cudaErrorInvalidValue;
+            bool done = false;
+            if (strided && engine != 1) {
+                TmaStep ts{src, dst, s.outer, s.n_in, s.inner, sc, s.swap ? 1 : 0};
+                e = pl->precision == 8 ? launch_tma_f64(n, variant_t, ts, st) : launch_tma_f32(n, variant_t, ts, st);
+                if (e == cudaErrorInvalidValue && variant_t != 0 && !strict)
+                    e = pl->precision == 8 ? launch_tma_f64(n, 0, ts, st) : launch_tma_f32(n, 0, ts, st);
+                done = (e != cudaErrorInvalidValue) || engine == 2;
+            }
+            if (!done) {
+                e = launch(var);
+                if (e == cudaErrorInvalidValue && var != 0 && !strict) e = launch(0);   // variant not built for this n
+            }
         } else {
             GenericParams g;
             memset(&g, 0, sizeof(g));

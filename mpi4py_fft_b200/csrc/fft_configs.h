@@ -1,41 +1,119 @@
-// fft_configs.h -- the one table of power-of-two kernel instances.
+// fft_configs.h -- the tables of power-of-two kernel instances.
 //
-// X(N, VAR, E, PC, PSC, PST, PSS, MINB, radices...)
+// One row = one compiled kernel:  X(N, VAR, E, P, PS, MINB, radices...)
 //   N      transform length
-//   VAR    variant id (0 = default; others selectable with b2f_set_option("variant", v))
+//   VAR    variant id (0 = default; others selectable with
+//          b2f_set_option("variant_contig" | "variant_strided", v) -- used by
+//          tools/sweep.py to pick the default on hardware)
 //   E      points held per thread            (threads per pencil = N/E)
-//   PC     pencils per CTA, contiguous axis  PSC  log2 pad period there (30 = none)
-//   PST    pencils per CTA, strided axis     PSS  log2 pad period there (30 = none)
+//   P      pencils per CTA tile              (threads per CTA = P*N/E)
+//   PS     log2 of the shared-memory pad period (one pad slot every 2^PS
+//          points; 30 = none)
 //   MINB   __launch_bounds__ min CTAs per SM (register cap)
-// The same table drives the kernels (fft_pow2_*.cu) and the CPU emulator
+// CONTIG tables serve the unit-stride axis (a tile is P rows of N points),
+// STRIDED tables every other axis (a tile is N rows of P contiguous elements;
+// P*itemsize is the contiguous run per row: it must be >= 128 B to stay off the
+// translation-rate limit when rows are more than a 2 MiB page apart, see
+// DESIGN.md "what the stride probe showed").
+// The same tables drive the kernels (fft_pow2_*.cu) and the CPU emulator
 // (tests/emu/emu_fft.cpp).
 #pragma once
 
-#define B2F_POW2_TABLE_SMALL(X)                    \
-    X(2, 0, 2, 128, 30, 128, 30, 1, 2)             \
-    X(4, 0, 4, 128, 30, 128, 30, 1, 4)             \
-    X(8, 0, 8, 64, 30, 64, 30, 1, 8)               \
-    X(16, 0, 16, 32, 30, 32, 30, 1, 16)            \
-    X(32, 0, 8, 32, 3, 32, 30, 1, 8, 4)            \
-    X(64, 0, 8, 16, 3, 16, 30, 1, 8, 8)            \
-    X(128, 0, 16, 16, 4, 16, 30, 1, 16, 8)         \
-    X(256, 0, 16, 8, 4, 8, 30, 1, 16, 16)
+#define B2F_CONTIG_SMALL(X)               \
+    X(2, 0, 2, 128, 30, 1, 2)             \
+    X(4, 0, 4, 128, 30, 1, 4)             \
+    X(8, 0, 8, 64, 30, 1, 8)              \
+    X(16, 0, 16, 32, 30, 1, 16)           \
+    X(32, 0, 8, 32, 3, 1, 8, 4)           \
+    X(64, 0, 8, 16, 3, 1, 8, 8)           \
+    X(128, 0, 16, 16, 4, 1, 16, 8)        \
+    X(256, 0, 16, 8, 4, 1, 16, 16)        \
+    X(256, 1, 16, 4, 4, 1, 16, 16)        \
+    X(256, 2, 16, 2, 4, 1, 16, 16)
 
-#define B2F_POW2_TABLE_MID(X)                      \
-    X(512, 0, 8, 4, 3, 4, 3, 2, 8, 8, 8)           \
-    X(512, 1, 16, 4, 3, 8, 30, 1, 8, 8, 8)         \
-    X(512, 2, 8, 2, 3, 8, 30, 1, 8, 8, 8)          \
-    X(1024, 0, 16, 4, 4, 4, 4, 2, 16, 8, 8)        \
-    X(1024, 1, 16, 2, 4, 8, 30, 1, 16, 8, 8)       \
-    X(1024, 2, 16, 1, 4, 2, 4, 1, 16, 8, 8)
+#define B2F_STRIDED_SMALL(X)              \
+    X(2, 0, 2, 128, 30, 1, 2)             \
+    X(4, 0, 4, 128, 30, 1, 4)             \
+    X(8, 0, 8, 64, 30, 1, 8)              \
+    X(16, 0, 16, 32, 30, 1, 16)           \
+    X(32, 0, 8, 32, 30, 1, 8, 4)          \
+    X(64, 0, 8, 16, 30, 1, 8, 8)          \
+    X(128, 0, 16, 16, 30, 1, 16, 8)       \
+    X(256, 0, 16, 8, 30, 1, 16, 16)       \
+    X(256, 1, 16, 16, 30, 1, 16, 16)      \
+    X(256, 2, 16, 32, 30, 1, 16, 16)
 
-#define B2F_POW2_TABLE_LARGE(X)                    \
-    X(2048, 0, 16, 2, 4, 2, 4, 1, 16, 16, 8)       \
-    X(2048, 1, 16, 1, 4, 4, 4, 1, 16, 16, 8)       \
-    X(4096, 0, 16, 1, 4, 2, 4, 1, 16, 16, 16)      \
-    X(8192, 0, 16, 1, 4, 1, 4, 1, 16, 8, 8, 8)
+#define B2F_CONTIG_MID(X)                 \
+    X(512, 0, 16, 4, 3, 1, 8, 8, 8)       \
+    X(512, 1, 8, 4, 3, 2, 8, 8, 8)        \
+    X(512, 2, 8, 2, 3, 4, 8, 8, 8)        \
+    X(512, 3, 8, 1, 3, 8, 8, 8, 8)        \
+    X(512, 4, 16, 2, 3, 1, 8, 8, 8)       \
+    X(512, 5, 16, 8, 3, 1, 8, 8, 8)       \
+    X(512, 6, 32, 8, 5, 1, 32, 16)        \
+    X(512, 7, 32, 4, 5, 1, 32, 16)        \
+    X(1024, 0, 16, 1, 4, 1, 16, 8, 8)     \
+    X(1024, 1, 16, 2, 4, 1, 16, 8, 8)     \
+    X(1024, 2, 16, 4, 4, 2, 16, 8, 8)     \
+    X(1024, 3, 32, 4, 5, 1, 32, 32)       \
+    X(1024, 4, 32, 2, 5, 1, 32, 32)       \
+    X(1024, 5, 32, 1, 5, 1, 32, 32)       \
+    X(1024, 6, 16, 8, 4, 1, 16, 8, 8)     \
+    X(1024, 7, 16, 4, 3, 2, 8, 8, 16)
 
-#define B2F_POW2_TABLE_ALL(X) \
-    B2F_POW2_TABLE_SMALL(X) B2F_POW2_TABLE_MID(X) B2F_POW2_TABLE_LARGE(X)
+#define B2F_STRIDED_MID(X)                \
+    X(512, 0, 16, 8, 30, 1, 8, 8, 8)      \
+    X(512, 1, 8, 4, 3, 2, 8, 8, 8)        \
+    X(512, 2, 8, 8, 30, 1, 8, 8, 8)       \
+    X(512, 3, 16, 16, 30, 1, 8, 8, 8)     \
+    X(512, 4, 16, 4, 3, 1, 8, 8, 8)       \
+    X(512, 5, 32, 8, 30, 1, 32, 16)       \
+    X(512, 6, 32, 16, 30, 1, 32, 16)      \
+    X(1024, 0, 16, 8, 30, 1, 16, 8, 8)    \
+    X(1024, 1, 16, 4, 4, 2, 16, 8, 8)     \
+    X(1024, 2, 32, 8, 30, 1, 32, 32)      \
+    X(1024, 3, 32, 4, 5, 1, 32, 32)       \
+    X(1024, 4, 16, 4, 4, 1, 16, 8, 8)
+
+#define B2F_CONTIG_LARGE(X)               \
+    X(2048, 0, 16, 2, 4, 1, 16, 16, 8)    \
+    X(2048, 1, 16, 1, 4, 1, 16, 16, 8)    \
+    X(4096, 0, 16, 1, 4, 1, 16, 16, 16)   \
+    X(8192, 0, 16, 1, 4, 1, 16, 8, 8, 8)
+
+#define B2F_STRIDED_LARGE(X)              \
+    X(2048, 0, 16, 2, 4, 1, 16, 16, 8)    \
+    X(2048, 1, 16, 4, 4, 1, 16, 16, 8)    \
+    X(4096, 0, 16, 2, 4, 1, 16, 16, 16)   \
+    X(8192, 0, 16, 1, 4, 1, 16, 8, 8, 8)
+
+// TMA-staged strided kernels (fft_tma.cuh):
+//   X(N, VAR, E, P, PS, STAGES, SPLIT, MINB, radices...)
+//   STAGES  shared-memory stages the TMA engine fills ahead of the compute
+//   SPLIT   1 = the exchange buffer holds one real component at a time
+//   PS      pad period of the exchange buffer (rows narrower than 128 B need
+//           log2(first radix); 30 = none)
+#define B2F_TMA_TABLE(X)                           \
+    X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8)             \
+    X(128, 0, 16, 16, 30, 2, 0, 1, 16, 8)          \
+    X(128, 1, 16, 8, 30, 2, 0, 1, 16, 8)           \
+    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)          \
+    X(256, 1, 16, 16, 30, 2, 0, 1, 16, 16)         \
+    X(512, 0, 16, 8, 3, 1, 1, 2, 8, 8, 8)          \
+    X(512, 1, 32, 8, 5, 1, 1, 1, 32, 16)           \
+    X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8)         \
+    X(512, 3, 16, 4, 3, 2, 0, 1, 8, 8, 8)          \
+    X(512, 4, 8, 8, 3, 1, 1, 1, 8, 8, 8)           \
+    X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16)          \
+    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
+    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
+    X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8)        \
+    X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32)          \
+    X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8)        \
+    X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32)          \
+    X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
+
+#define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X)
+#define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X)
 
 #define B2F_POW2_MAX_N 8192

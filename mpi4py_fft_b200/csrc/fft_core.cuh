@@ -6,6 +6,10 @@
 // involved.  Replaces the FFTW codelets behind fftw_plan_guru_dft
 // (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:52-56).
 #pragma once
+#ifndef B2F_TW_POW2
+#define B2F_TW_POW2 1
+#endif
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -133,7 +137,43 @@ struct Radices {
         for (int i = 0; i < s; ++i) p *= r[i];
         return p;
     }
+    // Twiddle storage: one table per pass s >= 1, laid out [r-1][k] with
+    // k = 0..Ns-1 fastest, entry = W_{Ns*R}^{r*k}.  Consecutive butterflies of a
+    // pass (consecutive lanes) read consecutive k, so a warp's twiddle load is
+    // one coalesced run instead of a gather over a single length-N table.
+    static B2F_HDC int tw_offset(int s) {
+        int off = 0;
+        constexpr int r[sizeof...(Rs)] = {Rs...};
+        int ns = r[0];
+        for (int i = 1; i < s; ++i) {
+            off += (r[i] - 1) * ns;
+            ns *= r[i];
+        }
+        return off;
+    }
+    static B2F_HDC int tw_total() { return tw_offset((int)sizeof...(Rs)) > 0 ? tw_offset((int)sizeof...(Rs)) : 1; }
 };
+
+// host: fill the per-pass twiddle tables of a radix schedule (long double angles)
+template <class T, class RAD>
+inline void build_pass_twiddles(cplx<T>* out) {
+    const long double TWO_PI = 6.28318530717958647692528676655900577L;
+    out[0].x = (T)1;
+    out[0].y = (T)0;
+    int ns = RAD::get(0);
+    for (int s = 1; s < RAD::count; ++s) {
+        const int R = RAD::get(s);
+        cplx<T>* t = out + RAD::tw_offset(s);
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < ns; ++k) {
+                const long long num = ((long long)r * k) % ((long long)ns * R);
+                const long double a = TWO_PI * (long double)num / (long double)((long long)ns * R);
+                t[(r - 1) * ns + k].x = (T)cosl(a);
+                t[(r - 1) * ns + k].y = (T)(-sinl(a));
+            }
+        ns *= R;
+    }
+}
 
 // shared-memory index of point i of pencil p inside a CTA tile.
 //   CONTIG : pencils are separate rows, row pitch PITCH, one pad slot every
@@ -168,7 +208,12 @@ struct SmemIndex {
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS>
 struct TileFFT {
     using C = cplx<T>;
+    using Real = T;
+    using RADS = RAD;
     using SI = SmemIndex<STRIDED, P, N, PS>;
+    static constexpr int LEN = N;
+    static constexpr int EPT = E;              // points per thread
+    static constexpr int PEN = P;              // pencils per tile
     static constexpr int TP = N / E;           // threads per pencil
     static constexpr int THREADS = TP * P;
     static constexpr int NPASS = RAD::count;
@@ -179,23 +224,61 @@ struct TileFFT {
     static B2F_HD int pencil_of(int tid) { return STRIDED ? tid % P : tid / TP; }
     static B2F_HD int slot_of(int tid) { return STRIDED ? tid / P : tid % TP; }
 
+    // twiddles of one butterfly: W^r, r = 1..R-1, for k fixed.  Only the powers
+    // of two are loaded (log2 R coalesced loads instead of R-1); the rest are
+    // products of at most three loaded values (<= 2 roundings deep), which
+    // keeps the L1 wavefront count of the twiddle traffic below the data's.
+    template <int R, int Ns>
+    static B2F_HD void apply_twiddles(C* v, const C* __restrict__ t) {
+#if B2F_TW_POW2
+        if constexpr (R <= 4) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], t[(r - 1) * Ns]);
+        } else {
+            // r = 8a + b: lo[b] = W^b (b < 8), hi = W^(8a)
+            C lo[8];
+            lo[1] = t[0];
+            lo[2] = t[Ns];
+            lo[4] = t[3 * Ns];
+            lo[3] = cmul(lo[2], lo[1]);
+            lo[5] = cmul(lo[4], lo[1]);
+            lo[6] = cmul(lo[4], lo[2]);
+            lo[7] = cmul(lo[4], lo[3]);
+#pragma unroll
+            for (int b = 1; b < 8; ++b) v[b] = cmul(v[b], lo[b]);
+            if constexpr (R > 8) {
+                C w8 = t[7 * Ns];
+                C hi = w8;
+#pragma unroll
+                for (int a = 1; a < R / 8; ++a) {
+                    if (a == 2) hi = t[15 * Ns];          // W^16 is in the table
+                    else if (a == 3) hi = cmul(hi, w8);   // W^24 = W^16 * W^8
+                    v[8 * a] = cmul(v[8 * a], hi);
+#pragma unroll
+                    for (int b = 1; b < 8; ++b) v[8 * a + b] = cmul(v[8 * a + b], cmul(hi, lo[b]));
+                }
+            }
+        }
+#else
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[r] = cmul(v[r], t[(r - 1) * Ns]);
+#endif
+    }
+
     template <int S>
     static B2F_HD void twiddle_dft(C* v, int q, const C* __restrict__ tw) {
         constexpr int R = RAD::get(S);
         constexpr int Ns = RAD::before(S);
         constexpr int NB = E / R;
         static_assert(E % R == 0, "radix must divide E");
+        static_assert(R <= 32, "radix above 32 is not implemented");
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if (S > 0) {
                 const int j = q + b * TP;
                 const int k = j % Ns;
-                constexpr int tstride = N / (Ns * R);
-#pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    const C w = tw[r * k * tstride];
-                    v[b * R + r] = cmul(v[b * R + r], w);
-                }
+                constexpr int OFF = RAD::tw_offset(S);
+                apply_twiddles<R, Ns>(v + b * R, tw + OFF + k);
             }
             DftReg<R, T>::run(v + b * R);
         }

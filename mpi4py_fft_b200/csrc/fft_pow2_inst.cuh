@@ -1,13 +1,36 @@
 // fft_pow2_inst.cuh -- turns rows of fft_configs.h into launchers.
-// Each fft_pow2_<group>.cu includes this with B2F_INST_TABLE / B2F_INST_NAME set
-// so that the (large, fully unrolled) kernels compile in parallel.
+// Each fft_pow2_<group>_<prec>.cu includes this and expands the CONTIG and
+// STRIDED tables of its size group, so that the (large, fully unrolled) kernels
+// compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
 #include "fft_pow2.cuh"
 #include "fft_configs.h"
 #include "internal.h"
 
 namespace b2f {
+
+// per-pass twiddle tables of one radix schedule, uploaded once per device
+template <class T, class RAD>
+static const void* pass_twiddles() {
+    static std::mutex mu;
+    static const void* cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    const void*& slot = cache[dev & 63];
+    if (!slot) {
+        std::vector<cplx<T>> h((size_t)RAD::tw_total());
+        build_pass_twiddles<T, RAD>(h.data());
+        void* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(cplx<T>)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        slot = d;
+    }
+    return slot;
+}
 
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
 static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStream_t st) {
@@ -23,6 +46,8 @@ static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStre
         attr_done = true;
     }
     FftParams prm = prm_in;
+    prm.tw = pass_twiddles<T, RAD>();
+    if (!prm.tw) return cudaErrorMemoryAllocation;
     long long grid;
     if (STRIDED) {
         prm.tiles_per_outer = (prm.inner + P - 1) / P;
@@ -37,11 +62,26 @@ static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStre
     return cudaGetLastError();
 }
 
-#define B2F_INST_ROW(N, VAR, E, PC, PSC, PST, PSS, MINB, ...)                                        \
-    if (n == N && var == VAR) {                                                                      \
-        using RAD = Radices<__VA_ARGS__>;                                                            \
-        return strided ? launch_one<T, N, E, RAD, PST, true, PSS, MINB>(prm, outer, st)              \
-                       : launch_one<T, N, E, RAD, PC, false, PSC, MINB>(prm, outer, st);             \
+// strided tiles are sized in bytes: a float tile takes twice the pencils of a
+// double tile, so that a row of the tile is the same contiguous run in HBM
+template <class T> struct StridedScale { static constexpr int value = (int)(sizeof(double) / sizeof(T)); };
+
+#define B2F_INST_CONTIG(N, VAR, E, P, PS, MINB, ...)                                        \
+    if (n == N && var == VAR)                                                               \
+        return launch_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB>(prm, outer, st);
+#define B2F_INST_STRIDED(N, VAR, E, P, PS, MINB, ...)                                       \
+    if (n == N && var == VAR)                                                               \
+        return launch_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB>(prm, outer, st);
+
+#define B2F_DEFINE_GROUP(FN, T_, CONTIG_TABLE, STRIDED_TABLE)                                               \
+    cudaError_t FN(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st) { \
+        using T = T_;                                                                                       \
+        if (strided) {                                                                                      \
+            STRIDED_TABLE(B2F_INST_STRIDED)                                                                 \
+        } else {                                                                                            \
+            CONTIG_TABLE(B2F_INST_CONTIG)                                                                   \
+        }                                                                                                   \
+        return cudaErrorInvalidValue;                                                                       \
     }
 
 }  // namespace b2f

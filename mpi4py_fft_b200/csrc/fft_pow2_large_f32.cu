@@ -1,9 +1,5 @@
-// generated shape: instances of fft_pow2_kernel for the "large" size group, float
+// instances of fft_pow2_kernel for the "large" size group, float
 #include "fft_pow2_inst.cuh"
 namespace b2f {
-cudaError_t launch_pow2_large_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st) {
-    using T = float;
-    B2F_POW2_TABLE_LARGE(B2F_INST_ROW)
-    return cudaErrorInvalidValue;
-}
+B2F_DEFINE_GROUP(launch_pow2_large_f32, float, B2F_CONTIG_LARGE, B2F_STRIDED_LARGE)
 }  // namespace b2f

@@ -1,9 +1,5 @@
-// generated shape: instances of fft_pow2_kernel for the "small" size group, double
+// instances of fft_pow2_kernel for the "small" size group, double
 #include "fft_pow2_inst.cuh"
 namespace b2f {
-cudaError_t launch_pow2_small_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st) {
-    using T = double;
-    B2F_POW2_TABLE_SMALL(B2F_INST_ROW)
-    return cudaErrorInvalidValue;
-}
+B2F_DEFINE_GROUP(launch_pow2_small_f64, double, B2F_CONTIG_SMALL, B2F_STRIDED_SMALL)
 }  // namespace b2f

@@ -1,0 +1,230 @@
+// fft_tma.cuh -- strided-axis c2c Stockham kernel with TMA-staged tiles (sm_100a).
+//
+// The register-path kernel (fft_pow2.cuh) keeps a tile's points in registers
+// while its loads are in flight, so a CTA cannot compute and load at once and
+// big tiles (N x 128 B = 64..128 KiB) leave room for one or two CTAs per SM:
+// the strided axes ran latency-bound at 55-75 % of the HBM roofline.  Here a
+// persistent CTA owns a ring of shared-memory stages that the TMA engine fills
+// (cp.async.bulk.tensor, one box of P contiguous elements x <=256 rows per
+// request, completion on an mbarrier) while the threads transform the previous
+// tile:
+//
+//   TMA  : HBM --box--> stage[s]                      (async, no registers, no LSU)
+//   pass0: stage[s] -> registers -> R0-point DFTs     (stage s is free again:
+//          the next tile's box loads are issued right here)
+//   mid  : registers <-> exchange buffer (padded), twiddle, DFT
+//   last : registers -> HBM, normalisation fused      (coalesced 128 B runs)
+//
+// With SPLIT the exchange buffer holds one real component at a time (re, then
+// im), halving its footprint so that a 128 KiB tile (N = 1024, complex128, 128 B
+// rows) still fits next to its stage.  Backward = forward with re/im swapped on
+// the way in and out, as in fft_pow2.cuh.
+//
+// Replaces fftw_execute_dft on plans with is/os > 1
+// (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:52-56, fftw_xfftn.pyx:29-30).
+#pragma once
+#include <type_traits>
+#if defined(__CUDACC__)
+#include <cuda.h>
+#endif
+#include "fft_core.cuh"
+
+namespace b2f {
+
+struct TmaParams {
+    void* out;
+    const void* tw;
+    long long out_ostride;   // elements between consecutive outer indices
+    long long out_nstride;   // elements between consecutive points of a pencil
+    long long inner;         // extent of the contiguous inner index
+    long long tiles_per_outer;
+    long long ntiles;
+    double scale;
+    int swap;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+#endif  // __CUDACC__
+
+// exchange-buffer element: the complex value, or one real component (SPLIT)
+template <class TF, bool SPLIT>
+struct Exchange {
+    using C = typename TF::C;
+    using T = typename TF::Real;
+    using SI = typename TF::SI;
+    using X = typename std::conditional<SPLIT, T, C>::type;
+    static constexpr size_t bytes = sizeof(X) * (size_t)SI::tile_elems;
+
+    // registers (after pass S) -> buffer, component c (ignored unless SPLIT)
+    template <int S>
+    static B2F_HD void put(const C* v, int p, int q, X* buf, int c) {
+        constexpr int R = TF::RADS::get(S);
+        constexpr int Ns = TF::RADS::before(S);
+        constexpr int NB = TF::EPT / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = q + b * TF::TP;
+            const int base = (j / Ns) * (Ns * R) + (j % Ns);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if constexpr (SPLIT) buf[SI::at(p, base + r * Ns)] = c ? v[b * R + r].y : v[b * R + r].x;
+                else buf[SI::at(p, base + r * Ns)] = v[b * R + r];
+            }
+        }
+    }
+    // buffer -> registers (before pass S)
+    template <int S>
+    static B2F_HD void get(C* v, int p, int q, const X* buf, int c) {
+        constexpr int R = TF::RADS::get(S);
+        constexpr int NB = TF::EPT / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = q + b * TF::TP + r * (TF::LEN / R);
+                if constexpr (SPLIT) {
+                    if (c) v[b * R + r].y = buf[SI::at(p, i)];
+                    else v[b * R + r].x = buf[SI::at(p, i)];
+                } else {
+                    v[b * R + r] = buf[SI::at(p, i)];
+                }
+            }
+        }
+    }
+};
+
+// pass-0 read of a dense [N][P] stage (what a TMA box load leaves behind)
+template <class TF>
+static B2F_HD void load_stage(typename TF::C* v, int p, int q, const typename TF::C* stage, bool swap) {
+    using C = typename TF::C;
+    constexpr int R = TF::RADS::get(0);
+    constexpr int NB = TF::EPT / R;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = q + b * TF::TP + r * (TF::LEN / R);
+            C a = stage[n * TF::PEN + p];
+            if (swap) { auto t = a.x; a.x = a.y; a.y = t; }
+            v[b * R + r] = a;
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+
+template <class TF, class EX, int S>
+struct TmaMid {
+    using C = typename TF::C;
+    static __device__ __forceinline__ void run(C* v, int p, int q, typename EX::X* xbuf, const C* __restrict__ tw, bool split) {
+        if constexpr (S < TF::NPASS) {
+            // exchange between pass S-1 and pass S (the caller's values are post pass S-1)
+            EX::template put<S - 1>(v, p, q, xbuf, 0);
+            __syncthreads();
+            EX::template get<S>(v, p, q, xbuf, 0);
+            if (split) {
+                __syncthreads();
+                EX::template put<S - 1>(v, p, q, xbuf, 1);
+                __syncthreads();
+                EX::template get<S>(v, p, q, xbuf, 1);
+            }
+            TF::template twiddle_dft<S>(v, q, tw);
+            if constexpr (S + 1 < TF::NPASS) __syncthreads();   // buffer is rewritten by the next exchange
+            TmaMid<TF, EX, S + 1>::run(v, p, q, xbuf, tw, split);
+        }
+    }
+};
+
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB)
+fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
+    using TF = TileFFT<T, N, E, RAD, P, true, PS>;
+    using EX = Exchange<TF, SPLIT>;
+    using C = cplx<T>;
+    constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(C) * N * P);
+    constexpr int BR = N > 256 ? 256 : N;          // rows per TMA box (box dims are capped at 256)
+    extern __shared__ __align__(1024) unsigned char b2f_tma_smem[];
+    __shared__ uint64_t full[STAGES];
+    C* stages = reinterpret_cast<C*>(b2f_tma_smem);
+    typename EX::X* xbuf = reinterpret_cast<typename EX::X*>(b2f_tma_smem + (size_t)STAGES * TILE_BYTES);
+
+    const int tid = threadIdx.x;
+    const int p = TF::pencil_of(tid);
+    const int q = TF::slot_of(tid);
+    const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
+    const bool swap = prm.swap != 0;
+    const long long first = blockIdx.x, step = gridDim.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](long long t, int s) {
+        const long long o = t / prm.tiles_per_outer;
+        const long long i0 = (t - o * prm.tiles_per_outer) * P;
+        mbar_expect_tx(&full[s], TILE_BYTES);
+        unsigned char* dst = b2f_tma_smem + (size_t)s * TILE_BYTES;
+#pragma unroll
+        for (int r = 0; r < N; r += BR)
+            tma_load_3d(dst + (size_t)r * P * sizeof(C), &map_in, (int)(2 * i0), r, (int)o, &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (first + s * step < prm.ntiles) issue(first + s * step, s);
+    }
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (long long t = first; t < prm.ntiles; t += step) {
+        const long long o = t / prm.tiles_per_outer;
+        const long long i = (t - o * prm.tiles_per_outer) * P + p;
+        const bool valid = i < prm.inner;
+        C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
+
+        C v[E];
+        mbar_wait(&full[s], parity);
+        load_stage<TF>(v, p, q, stages + (size_t)s * N * P, swap);
+        __syncthreads();   // every thread has read stage s (and finished with the exchange buffer of the previous tile)
+        if (tid == 0 && t + (long long)STAGES * step < prm.ntiles) issue(t + (long long)STAGES * step, s);
+        TF::template twiddle_dft<0>(v, q, tw);
+        TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT);
+        TF::store_global(v, q, gout, prm.out_nstride, valid, swap, (T)prm.scale);
+        if (++s == STAGES) {
+            s = 0;
+            parity ^= 1;
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2f

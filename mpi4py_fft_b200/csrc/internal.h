@@ -23,12 +23,25 @@ cudaError_t launch_pow2_small_f32(int n, int var, bool strided, const FftParams&
 cudaError_t launch_pow2_mid_f32  (int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_pow2_large_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 
+// TMA-staged strided c2c kernels (fft_tma_*.cu): one (outer, n, inner) step.
+// cudaErrorInvalidValue = (n, var) not built or the layout cannot be described
+// to TMA (16-byte base and row pitch); the caller then uses the register path.
+struct TmaStep {
+    const void* in;
+    void* out;
+    long long outer, n, inner;
+    double scale;
+    int swap;
+};
+cudaError_t launch_tma_f64(int n, int var, const TmaStep& st, cudaStream_t stream);
+cudaError_t launch_tma_f32(int n, int var, const TmaStep& st, cudaStream_t stream);
+int sm_count();   // SMs of the current device (cached)
+
 // generic (any n, any kind) dense-matrix path, dft_generic.cu
 struct GenericParams;
 int build_matrix(int kind, long long n, std::vector<double>& M, long long& rows, long long& cols);
 
-// twiddle / matrix caches (capi.cu); device pointers live until process exit
-const void* twiddle_table(int n, int precision);          // n forward twiddles
+// matrix cache (capi.cu); device pointers live until process exit
 const double* generic_matrix(int kind, long long n, int* rows, int* cols);
 
 }  // namespace b2f

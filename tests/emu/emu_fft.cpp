@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../mpi4py_fft_b200/csrc/fft_core.cuh"
 #include "../../mpi4py_fft_b200/csrc/fft_pow2.cuh"
+#include "../../mpi4py_fft_b200/csrc/fft_tma.cuh"
 #include "../../mpi4py_fft_b200/csrc/fft_configs.h"
 
 using namespace b2f;
@@ -52,7 +53,9 @@ static int emu_one(const FftParams& prm_in, long long outer) {
     } else {
         grid = (prm.npencils + P - 1) / P;
     }
-    const C* tw = reinterpret_cast<const C*>(prm.tw);
+    std::vector<C> twv((size_t)RAD::tw_total());
+    build_pass_twiddles<T, RAD>(twv.data());   // same host builder as the library (fft_core.cuh)
+    const C* tw = twv.data();
     const bool swap = prm.swap != 0;
     std::vector<C> smem((size_t)TF::SI::tile_elems);
     std::vector<C> regs((size_t)TF::THREADS * E);
@@ -109,17 +112,109 @@ static int emu_one(const FftParams& prm_in, long long outer) {
     return 0;
 }
 
-#define EMU_ROW(N, VAR, E, PC, PSC, PST, PSS, MINB, ...)                                  \
-    if (n == N && var == VAR) {                                                           \
-        using RAD = Radices<__VA_ARGS__>;                                                 \
-        return strided ? emu_one<T, N, E, RAD, PST, true, PSS>(prm, outer)                \
-                       : emu_one<T, N, E, RAD, PC, false, PSC>(prm, outer);               \
-    }
+#define EMU_CONTIG(N, VAR, E, P, PS, MINB, ...) \
+    if (n == N && var == VAR) return emu_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS>(prm, outer);
+// float strided tiles hold twice the pencils (same bytes per row), as in fft_pow2_inst.cuh
+#define EMU_STRIDED(N, VAR, E, P, PS, MINB, ...) \
+    if (n == N && var == VAR)                    \
+        return emu_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS>(prm, outer);
 
 template <class T>
 static int emu_dispatch(int n, int var, bool strided, const FftParams& prm, long long outer) {
-    B2F_POW2_TABLE_ALL(EMU_ROW)
+    if (strided) {
+        B2F_STRIDED_ALL(EMU_STRIDED)
+    } else {
+        B2F_CONTIG_ALL(EMU_CONTIG)
+    }
     return -1;
+}
+
+// ---- TMA-staged strided kernel (fft_tma.cuh): the box load is emulated by a
+// dense copy with zero fill outside the array, everything after it is the
+// kernel's own per-thread code with its barriers.
+template <class TF, class EX, int S>
+struct EmuTmaMid {
+    using C = typename TF::C;
+    static void run(std::vector<C>& regs, typename EX::X* xbuf, const C* tw, bool split) {
+        if constexpr (S < TF::NPASS) {
+            const int nthr = TF::THREADS, E = TF::EPT;
+            for (int c = 0; c < (split ? 2 : 1); ++c) {
+                for (int tid = 0; tid < nthr; ++tid)
+                    EX::template put<S - 1>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), xbuf, c);
+                // __syncthreads()
+                for (int tid = 0; tid < nthr; ++tid)
+                    EX::template get<S>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), xbuf, c);
+                // __syncthreads()
+            }
+            for (int tid = 0; tid < nthr; ++tid)
+                TF::template twiddle_dft<S>(&regs[(size_t)tid * E], TF::slot_of(tid), tw);
+            EmuTmaMid<TF, EX, S + 1>::run(regs, xbuf, tw, split);
+        }
+    }
+};
+
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT>
+static int emu_tma_one(const FftParams& prm, long long outer) {
+    using TF = TileFFT<T, N, E, RAD, P, true, PS>;
+    using EX = Exchange<TF, SPLIT>;
+    using C = cplx<T>;
+    const long long tpo = (prm.inner + P - 1) / P, ntiles = outer * tpo;
+    std::vector<C> twv((size_t)RAD::tw_total());
+    build_pass_twiddles<T, RAD>(twv.data());
+    std::vector<C> stage((size_t)N * P);
+    std::vector<typename EX::X> xbuf((size_t)TF::SI::tile_elems);
+    std::vector<C> regs((size_t)TF::THREADS * E);
+    const C* gin = reinterpret_cast<const C*>(prm.in);
+    C* gout = reinterpret_cast<C*>(prm.out);
+    const bool swap = prm.swap != 0;
+    for (long long t = 0; t < ntiles; ++t) {
+        const long long o = t / tpo, i0 = (t - o * tpo) * P;
+        for (int n = 0; n < N; ++n)
+            for (int pp = 0; pp < P; ++pp) {
+                C z = {(T)0, (T)0};
+                stage[(size_t)n * P + pp] = (i0 + pp < prm.inner) ? gin[o * prm.in_ostride + (long long)n * prm.in_nstride + i0 + pp] : z;
+            }
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            C* v = &regs[(size_t)tid * E];
+            load_stage<TF>(v, TF::pencil_of(tid), TF::slot_of(tid), stage.data(), swap);
+        }
+        // __syncthreads(); next box load is issued here
+        for (auto& x : xbuf) x = typename EX::X{};
+        for (int tid = 0; tid < TF::THREADS; ++tid)
+            TF::template twiddle_dft<0>(&regs[(size_t)tid * E], TF::slot_of(tid), twv.data());
+        EmuTmaMid<TF, EX, 1>::run(regs, xbuf.data(), twv.data(), SPLIT);
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            const long long i = i0 + TF::pencil_of(tid);
+            TF::store_global(&regs[(size_t)tid * E], TF::slot_of(tid), gout + o * prm.out_ostride + i, prm.out_nstride,
+                             i < prm.inner, swap, (T)prm.scale);
+        }
+    }
+    return 0;
+}
+
+#define EMU_TMA(N, VAR, E, P, PS, STAGES, SPLIT, MINB, ...) \
+    if (n == N && var == VAR)                                \
+        return emu_tma_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), PS, STAGES, SPLIT != 0>(prm, outer);
+
+template <class T>
+static int emu_tma_dispatch(int n, int var, const FftParams& prm, long long outer) {
+    B2F_TMA_TABLE(EMU_TMA)
+    return -1;
+}
+
+extern "C" int emu_fft_tma(int precision, int n, int var, long long outer, long long inner, const void* in, void* out,
+                           double scale, int swap) {
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.in = in;
+    prm.out = out;
+    prm.scale = scale;
+    prm.swap = swap;
+    prm.in_ostride = prm.out_ostride = (long long)n * inner;
+    prm.in_nstride = prm.out_nstride = inner;
+    prm.inner = inner;
+    if (precision == 8) return emu_tma_dispatch<double>(n, var, prm, outer);
+    return emu_tma_dispatch<float>(n, var, prm, outer);
 }
 
 // (outer, n, inner) C-contiguous block, transform along the middle axis.

@@ -76,7 +76,7 @@ def test_stockham_pow2_c2c(B, n, dt):
     tol = TOL[dt.lower()]
     shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 2048 else [(2, n), (n, 5)]
     try:
-        for variant in range(3):
+        for variant in range(8):
             _lib.set_option('variant', variant)
             for shape in shapes:
                 axis = shape.index(n)
@@ -98,6 +98,57 @@ def test_stockham_pow2_c2c(B, n, dt):
                 assert relerr(V, ref * n) < tol, ('inplace', n, dt, variant, shape)
     finally:
         _lib.set_option('variant', 0)
+
+
+@pytest.mark.parametrize('n', [64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize('dt', ['D', 'F'])
+def test_tma_staged_strided_c2c(B, n, dt):
+    """strided axes through the TMA-staged persistent kernel (fft_tma.cuh), every
+    variant: several tiles per CTA, ragged last tile, outer > 1, backward,
+    fused normalisation, in place; then the automatic engine choice on a layout
+    TMA cannot describe (odd inner extent of complex64: 8-byte row pitch)."""
+    from mpi4py_fft_b200 import _lib
+    tol = TOL[dt.lower()]
+    big = 148 * 2 * 8 * 3 + 6 if n <= 512 else 148 * 8 + 6      # > one tile per persistent CTA
+    shapes = [(n, big), (3, n, 40), (2, n, 26)]
+    try:
+        _lib.set_option('strided_engine', 2)
+        _lib.set_option('variant_strict', 1)
+        for variant in range(6):
+            _lib.set_option('variant_tma', variant)
+            for shape in shapes:
+                axis = shape.index(n)
+                x = rand(shape, dt, seed=n + axis)
+                U = B.fftw.aligned(shape, dtype=dt)
+                U[...] = x
+                fwd = B.fftw.fftn(U, axes=(axis,))
+                try:
+                    y = fwd(normalize=True)
+                except Exception as exc:
+                    assert 'invalid' in str(exc).lower(), exc     # variant not built for this n
+                    break
+                ref = np.fft.fft(x.astype('D'), axis=axis) / n
+                assert relerr(y, ref) < tol, ('fwd', n, dt, variant, shape)
+                bck = B.fftw.ifftn(fwd.output_array, axes=(axis,), output_array=U)
+                z = bck()
+                assert relerr(z, x.astype('D')) < tol, ('bwd', n, dt, variant, shape)
+                V = B.fftw.aligned(shape, dtype=dt)
+                V[...] = x
+                B.fftw.fftn(V, axes=(axis,), output_array=V)()
+                assert relerr(V, ref * n) < tol, ('inplace', n, dt, variant, shape)
+        _lib.set_option('variant_strict', 0)
+        _lib.set_option('variant_tma', 0)
+        _lib.set_option('strided_engine', 0)
+        shape = (n, 33)
+        x = rand(shape, dt, seed=1)
+        U = B.fftw.aligned(shape, dtype=dt)
+        U[...] = x
+        y = B.fftw.fftn(U, axes=(0,))()
+        assert relerr(y, np.fft.fft(x.astype('D'), axis=0)) < tol
+    finally:
+        _lib.set_option('variant_strict', 0)
+        _lib.set_option('variant_tma', 0)
+        _lib.set_option('strided_engine', 1)
 
 
 @pytest.mark.parametrize('dt', ['d', 'f'])

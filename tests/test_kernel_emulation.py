@@ -28,7 +28,7 @@ def run(emu, prec, n, var, outer, inner, swap, scale, inplace, seed=0):
 def test_all_variants(emu, n, prec):
     tol = 2e-15 if prec == 8 else 2e-6
     found = 0
-    for var in range(4):
+    for var in range(8):
         for outer, inner in ((3, 1), (2, 5), (1, 17), (1, 1)):
             if n >= 2048 and (outer, inner) == (1, 17):
                 inner = 9
@@ -39,3 +39,34 @@ def test_all_variants(emu, n, prec):
                 found += 1
                 assert err < tol, (n, prec, var, outer, inner, swap, err)
     assert found >= 8
+
+
+def run_tma(emu, prec, n, var, outer, inner, swap, scale, inplace, seed=0):
+    rng = np.random.default_rng(seed)
+    ct = np.complex128 if prec == 8 else np.complex64
+    x = (rng.random((outer, n, inner)) + 1j * rng.random((outer, n, inner))).astype(ct)
+    xin = x.copy()
+    y = xin if inplace else np.full_like(x, np.nan)
+    rc = emu.emu_fft_tma(prec, n, var, outer, inner, xin.ctypes.data, y.ctypes.data, scale, swap)
+    if rc != 0:
+        return None
+    x64 = x.astype(np.complex128)
+    ref = (np.fft.ifft(x64, axis=1) * n if swap else np.fft.fft(x64, axis=1)) * scale
+    return np.abs(y - ref).max() / np.abs(ref).max()
+
+
+@pytest.mark.parametrize('n', [64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize('prec', [8, 4])
+def test_tma_staged_variants(emu, n, prec):
+    """fft_tma.cuh: stage read, split / unsplit exchange, ragged last tile"""
+    tol = 2e-15 if prec == 8 else 2e-6
+    found = 0
+    for var in range(8):
+        for outer, inner in ((2, 8), (1, 19)):
+            for swap in (0, 1):
+                err = run_tma(emu, prec, n, var, outer, inner, swap, 1.0 / n if swap else 1.0, inplace=bool(swap))
+                if err is None:
+                    continue
+                found += 1
+                assert err < tol, (n, prec, var, outer, inner, swap, err)
+    assert found >= 4

@@ -2,7 +2,7 @@
 three axes of an S^3 complex128 (or complex64) block; prints GB/s (algorithmic:
 one read + one write of the block) and the fraction of the measured HBM peak.
 
-    python tools/sweep.py [--size 512] [--dtype D] [--variants 0,1,2] [--reps 10]
+    python tools/sweep.py [--size 512] [--dtype D] [--variants 0-7] [--reps 10] [--shape a,b,c]
 """
 import argparse
 import json
@@ -16,11 +16,14 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--shape', default=None, help='a,b,c (overrides --size)')
     ap.add_argument('--dtype', default='D')
-    ap.add_argument('--variants', default='0,1,2')
+    ap.add_argument('--variants', default='0-7')
     ap.add_argument('--reps', type=int, default=10)
+    ap.add_argument('--axes', default='2,1,0')
+    ap.add_argument('--inplace', action='store_true')
+    ap.add_argument('--engine', default='reg', choices=['reg', 'tma'], help='strided axes: register path or TMA-staged')
     args = ap.parse_args()
-    import numpy as np
     import torch
     import mpi4py_fft_b200 as B
     from mpi4py_fft_b200 import _lib
@@ -31,13 +34,17 @@ def main():
     except Exception:
         pass
     S = args.size
-    shape = (S, S, S)
+    shape = (S, S, S) if args.shape is None else tuple(int(x) for x in args.shape.split(','))
+    if '-' in args.variants:
+        lo, hi = args.variants.split('-')
+        variants = list(range(int(lo), int(hi) + 1))
+    else:
+        variants = [int(v) for v in args.variants.split(',')]
     a = B.fftw.aligned(shape, dtype=args.dtype)
     b = B.fftw.aligned(shape, dtype=args.dtype)
     a.tensor.copy_(torch.view_as_complex(torch.rand(shape + (2,), dtype=a.tensor.real.dtype, device='cuda')))
     nbytes = 2.0 * a.nbytes
     stream = torch.cuda.current_stream()
-    # plain copy for reference
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         b.tensor.copy_(a.tensor)
@@ -48,15 +55,25 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
-    print("copy            %8.3f ms  %7.1f GB/s  %.3f of measured peak %.0f" % (ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / peak, peak))
-    rows = []
-    for axis in (2, 1, 0):
-        for var in [int(v) for v in args.variants.split(',')]:
-            _lib.set_option('variant', var)
-            for inplace in (False, True):
+    print("shape %s dtype %s" % (shape, args.dtype))
+    print("copy            %8.3f ms  %7.1f GB/s  %.3f of peak %.0f" % (ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / peak, peak))
+    _lib.set_option('variant_strict', 1)
+    nd = len(shape)
+    for axis in [int(x) for x in args.axes.split(',')]:
+        key = 'variant_contig' if axis == nd - 1 else 'variant_strided'
+        if axis != nd - 1:
+            _lib.set_option('strided_engine', 2 if args.engine == 'tma' else 1)
+            if args.engine == 'tma':
+                key = 'variant_tma'
+        for var in variants:
+            _lib.set_option(key, var)
+            for inplace in ((False, True) if args.inplace else (False,)):
                 plan = B.fftw.fftn(a, axes=(axis,), output_array=(a if inplace else b))
-                for _ in range(3):
-                    plan()
+                try:
+                    for _ in range(3):
+                        plan()
+                except Exception:
+                    break       # variant not built for this length
                 torch.cuda.synchronize()
                 e0.record(stream)
                 for _ in range(args.reps):
@@ -65,9 +82,11 @@ def main():
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / args.reps
                 gbs = nbytes / ms / 1e6
-                rows.append((axis, var, inplace, ms, gbs))
-                print("axis %d var %d %s %8.3f ms  %7.1f GB/s  %.3f" % (axis, var, 'inplace ' if inplace else 'outplace', ms, gbs, gbs / peak), flush=True)
-    _lib.set_option('variant', 0)
+                print("axis %d %s var %d %s %8.3f ms  %7.1f GB/s  %.3f" % (
+                    axis, key[8:], var, 'inplace ' if inplace else 'outplace', ms, gbs, gbs / peak), flush=True)
+        _lib.set_option(key, 0)
+    _lib.set_option('variant_strict', 0)
+    _lib.set_option('strided_engine', 1)
 
 
 if __name__ == '__main__':
