@@ -140,6 +140,30 @@ struct Step {
     int rows, cols;
 };
 
+// Default variant of the staged strided kernels (fft_configs.h B2F_TMA_TABLE /
+// 100 + B2F_CPA_TABLE) for a length and the distance between consecutive points
+// of a pencil; -1 = use the register-path kernel.  "hostile" rows sit in
+// different 2 MiB pages: every row of a tile costs an address translation, so
+// the widest tile that fits wins (stride probe).
+static int staged_default(int n, long long row_bytes) {
+    const bool hostile = row_bytes >= (2LL << 20);
+    switch (n) {
+        case 64: return 0;
+        case 128: return hostile ? 0 : 1;
+        case 256: return hostile ? 1 : 0;
+        case 512: return hostile ? 6 : 2;
+        case 1024: return 100;
+        case 2048: return 0;
+        default: return -1;
+    }
+}
+static int staged_fallback(int n) {
+    switch (n) {
+        case 256: case 512: case 1024: case 2048: return 100;
+        default: return -1;
+    }
+}
+
 static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 }  // namespace b2f
@@ -295,8 +319,8 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
     const int variant = (int)option("variant", 0);
     const int variant_c = (int)option("variant_contig", variant);
     const int variant_s = (int)option("variant_strided", variant);
-    const int variant_t = (int)option("variant_tma", 0);
-    const int engine = (int)option("strided_engine", 1);
+    const int variant_t = (int)option("variant_tma", -1);   // -1: chosen per step (staged_default)
+    const int engine = (int)option("strided_engine", 0);
     const bool strict = option("variant_strict", 0) != 0;
     const size_t nsteps = pl->steps.size();
     for (size_t si = 0; si < nsteps; ++si) {
@@ -340,9 +364,19 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
             bool done = false;
             if (strided && engine != 1) {
                 TmaStep ts{src, dst, s.outer, s.n_in, s.inner, sc, s.swap ? 1 : 0};
-                e = pl->precision == 8 ? launch_tma_f64(n, variant_t, ts, st) : launch_tma_f32(n, variant_t, ts, st);
-                if (e == cudaErrorInvalidValue && variant_t != 0 && !strict)
-                    e = pl->precision == 8 ? launch_tma_f64(n, 0, ts, st) : launch_tma_f32(n, 0, ts, st);
+                auto staged = [&](int v) {
+                    return pl->precision == 8 ? launch_tma_f64(n, v, ts, st) : launch_tma_f32(n, v, ts, st);
+                };
+                if (variant_t >= 0) {
+                    e = staged(variant_t);
+                } else {
+                    // measured defaults (profiles/r1_sweep*): first choice, then the
+                    // cp.async flavour for layouts a TMA descriptor cannot express
+                    const long long row_bytes = s.inner * 2LL * pl->precision;
+                    const int first = staged_default(n, row_bytes);
+                    e = first >= 0 ? staged(first) : cudaErrorInvalidValue;
+                    if (e == cudaErrorInvalidValue && first >= 0 && first < 100) e = staged(staged_fallback(n));
+                }
                 done = (e != cudaErrorInvalidValue) || engine == 2;
             }
             if (!done) {

@@ -105,12 +105,24 @@
     X(512, 3, 16, 4, 3, 2, 0, 1, 8, 8, 8)          \
     X(512, 4, 8, 8, 3, 1, 1, 1, 8, 8, 8)           \
     X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16)          \
+    X(512, 6, 32, 16, 5, 1, 1, 1, 32, 16)          \
+    X(512, 7, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
     X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
     X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
     X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8)        \
     X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32)          \
     X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8)        \
     X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32)          \
+    X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
+
+// the same pipeline filled by cp.async instead of TMA (variant_tma = 100 + VAR)
+#define B2F_CPA_TABLE(X)                           \
+    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)          \
+    X(512, 0, 16, 8, 30, 2, 0, 1, 8, 8, 8)         \
+    X(512, 1, 32, 16, 5, 1, 1, 1, 32, 16)          \
+    X(512, 2, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
+    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
+    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 #define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X)

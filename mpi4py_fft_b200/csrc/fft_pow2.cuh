@@ -47,8 +47,11 @@ struct MidPasses {
     }
 };
 
-template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftParams prm) {
+// SWAP is a compile-time constant inside the body so that the re/im exchange
+// of the backward transform costs no register moves around the 16-byte
+// loads/stores (the kernel branches once on prm.swap).
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, bool SWAP>
+__device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
     using C = cplx<T>;
     extern __shared__ __align__(16) unsigned char b2f_smem_raw[];
@@ -80,10 +83,9 @@ __global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftPa
         out_ns = 1;
     }
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
-    const bool swap = prm.swap != 0;
 
     C v[E];
-    TF::load_global(v, q, gin, in_ns, valid, swap);
+    TF::load_global(v, q, gin, in_ns, valid, SWAP);
     TF::template twiddle_dft<0>(v, q, tw);
     if constexpr (TF::NPASS > 1) {
         TF::template store_shared<0>(v, p, q, smem);
@@ -92,7 +94,13 @@ __global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftPa
         TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
         TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
     }
-    TF::store_global(v, q, gout, out_ns, valid, swap, (T)prm.scale);
+    TF::store_global(v, q, gout, out_ns, valid, SWAP, (T)prm.scale);
+}
+
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftParams prm) {
+    if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true>(prm);
+    else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false>(prm);
 }
 
 #endif  // __CUDACC__

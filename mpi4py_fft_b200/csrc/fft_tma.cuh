@@ -32,6 +32,8 @@
 namespace b2f {
 
 struct TmaParams {
+    const void* in;          // used by the cp.async loader only (TMA reads through its descriptor)
+    long long in_ostride, in_nstride;
     void* out;
     const void* tw;
     long long out_ostride;   // elements between consecutive outer indices
@@ -67,6 +69,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+// LOADER 1: the stage is filled with cp.async (LDGSTS) by all threads instead of
+// TMA boxes -- same asynchrony, goes through the LSU address path.  Serves the
+// layouts a TMA descriptor cannot express (8-byte row pitch) and rows that sit
+// in different 2 MiB pages, where the LSU path sustains more translations per
+// second than the TMA engine (tools/probe/stride_probe.cu).
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* dst, const void* src, bool valid) {
+    const int sz = valid ? BYTES : 0;   // src-size 0 -> zero fill
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
 }
 
 #endif  // __CUDACC__
@@ -160,9 +176,8 @@ struct TmaMid {
     }
 };
 
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB)
-fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP>
+__device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const TmaParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
     using C = cplx<T>;
@@ -177,15 +192,16 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) 
     const int p = TF::pencil_of(tid);
     const int q = TF::slot_of(tid);
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
-    const bool swap = prm.swap != 0;
     const long long first = blockIdx.x, step = gridDim.x;
 
-    if (tid == 0) {
+    if (LOADER == 0) {
+        if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     auto issue = [&](long long t, int s) {
         const long long o = t / prm.tiles_per_outer;
@@ -194,12 +210,34 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) 
         unsigned char* dst = b2f_tma_smem + (size_t)s * TILE_BYTES;
 #pragma unroll
         for (int r = 0; r < N; r += BR)
-            tma_load_3d(dst + (size_t)r * P * sizeof(C), &map_in, (int)(2 * i0), r, (int)o, &full[s]);
+            tma_load_3d(dst + (size_t)r * P * sizeof(C), map_in, (int)(2 * i0), r, (int)o, &full[s]);
     };
-    if (tid == 0) {
+    // cp.async flavour: every thread copies the E elements it will read back
+    // (row q + e*TP, column p); one commit group per tile slot, empty or not
+    auto issue_cpa = [&](long long t, int s) {
+        if (t < prm.ntiles) {
+            const long long o = t / prm.tiles_per_outer;
+            const long long i = (t - o * prm.tiles_per_outer) * P + p;
+            const bool ok = i < prm.inner;
+            const C* src = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + (ok ? i : 0);
+            C* dst = stages + (size_t)s * N * P + p;
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-            if (first + s * step < prm.ntiles) issue(first + s * step, s);
+            for (int e = 0; e < E; ++e) {
+                const int row = q + e * TF::TP;
+                cp_async_elem<(int)sizeof(C)>(dst + row * P, src + (long long)row * prm.in_nstride, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (LOADER == 0) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (first + s * step < prm.ntiles) issue(first + s * step, s);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) issue_cpa(first + s * step, s);
     }
 
     int s = 0;
@@ -211,18 +249,42 @@ fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) 
         C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
 
         C v[E];
-        mbar_wait(&full[s], parity);
-        load_stage<TF>(v, p, q, stages + (size_t)s * N * P, swap);
+        if (LOADER == 0) {
+            mbar_wait(&full[s], parity);
+        } else {
+            asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+            __syncthreads();   // everybody's copies of this tile have landed
+        }
+        load_stage<TF>(v, p, q, stages + (size_t)s * N * P, SWAP);
         __syncthreads();   // every thread has read stage s (and finished with the exchange buffer of the previous tile)
-        if (tid == 0 && t + (long long)STAGES * step < prm.ntiles) issue(t + (long long)STAGES * step, s);
+        if (LOADER == 0) {
+            if (tid == 0 && t + (long long)STAGES * step < prm.ntiles) issue(t + (long long)STAGES * step, s);
+        } else {
+            issue_cpa(t + (long long)STAGES * step, s);
+        }
         TF::template twiddle_dft<0>(v, q, tw);
         TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT);
-        TF::store_global(v, q, gout, prm.out_nstride, valid, swap, (T)prm.scale);
+        TF::store_global(v, q, gout, prm.out_nstride, valid, SWAP, (T)prm.scale);
         if (++s == STAGES) {
             s = 0;
             parity ^= 1;
         }
     }
+}
+
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB)
+fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true>(&map_in, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false>(&map_in, prm);
+}
+
+// the same pipeline with the cp.async loader (no descriptor)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB)
+fft_cpa_kernel(const TmaParams prm) {
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true>(nullptr, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false>(nullptr, prm);
 }
 
 #endif  // __CUDACC__

@@ -26,6 +26,52 @@ static bool tma_can_serve(const TmaStep& st) {
     return true;
 }
 
+static inline void fill_params(TmaParams& prm, const TmaStep& st, int P) {
+    prm.in = st.in;
+    prm.in_ostride = st.n * st.inner;
+    prm.in_nstride = st.inner;
+    prm.out = st.out;
+    prm.out_ostride = st.n * st.inner;
+    prm.out_nstride = st.inner;
+    prm.inner = st.inner;
+    prm.tiles_per_outer = (st.inner + P - 1) / P;
+    prm.ntiles = st.outer * prm.tiles_per_outer;
+    prm.scale = st.scale;
+    prm.swap = st.swap;
+}
+
+// cp.async-staged flavour: no descriptor, any layout whose elements are naturally aligned
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+static cudaError_t launch_cpa_one(const TmaStep& st, cudaStream_t stream) {
+    using TF = TileFFT<T, N, E, RAD, P, true, PS>;
+    using EX = Exchange<TF, SPLIT>;
+    auto kern = fft_cpa_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
+    constexpr size_t tile_bytes = sizeof(cplx<T>) * (size_t)N * P;
+    constexpr size_t smem = STAGES * tile_bytes + EX::bytes;
+    static_assert(smem <= 227 * 1024, "tile does not fit shared memory");
+    static int ctas_per_sm = 0;   // per instantiation
+    if (!ctas_per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TF::THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (nb < 1) return cudaErrorInvalidConfiguration;
+        ctas_per_sm = nb;
+    }
+    if (((uintptr_t)st.in | (uintptr_t)st.out) & (sizeof(cplx<T>) - 1)) return cudaErrorInvalidValue;
+    TmaParams prm;
+    fill_params(prm, st, P);
+    prm.tw = pass_twiddles<T, RAD>();
+    if (!prm.tw) return cudaErrorMemoryAllocation;
+    if (prm.ntiles <= 0) return cudaSuccess;
+    long long grid = (long long)sm_count() * ctas_per_sm;
+    if (grid > prm.ntiles) grid = prm.ntiles;
+    kern<<<(unsigned)grid, TF::THREADS, smem, stream>>>(prm);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
 static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
@@ -58,16 +104,9 @@ static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
     TmaParams prm;
-    prm.out = st.out;
+    fill_params(prm, st, P);
     prm.tw = pass_twiddles<T, RAD>();
     if (!prm.tw) return cudaErrorMemoryAllocation;
-    prm.out_ostride = st.n * st.inner;
-    prm.out_nstride = st.inner;
-    prm.inner = st.inner;
-    prm.tiles_per_outer = (st.inner + P - 1) / P;
-    prm.ntiles = st.outer * prm.tiles_per_outer;
-    prm.scale = st.scale;
-    prm.swap = st.swap;
     if (prm.ntiles <= 0) return cudaSuccess;
     long long grid = (long long)sm_count() * ctas_per_sm;
     if (grid > prm.ntiles) grid = prm.ntiles;
@@ -79,6 +118,11 @@ static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
 #define B2F_INST_TMA(N, VAR, E, P, PS, STAGES, SPLIT, MINB, ...)                                              \
     if (n == N && var == VAR)                                                                                 \
         return launch_tma_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, PS, STAGES, SPLIT != 0, \
+                              MINB>(st, stream);
+
+#define B2F_INST_CPA(N, VAR, E, P, PS, STAGES, SPLIT, MINB, ...)                                              \
+    if (n == N && var == 100 + VAR)                                                                           \
+        return launch_cpa_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, PS, STAGES, SPLIT != 0, \
                               MINB>(st, stream);
 
 }  // namespace b2f

@@ -194,7 +194,9 @@ static void run_tma(const char* tag, c128* in, c128* out, long long outer, long 
 
 int main(int argc, char** argv) {
     const long long S = argc > 1 ? atoll(argv[1]) : 512;
-    const long long total = S * S * S;
+    const long long pad = argc > 2 ? atoll(argv[2]) : 0;      // extra elements per axis-0 row (breaks the power-of-two stride)
+    const int quick = argc > 3 ? atoi(argv[3]) : 0;
+    const long long total = S * (S * S + pad);
     c128 *a, *b;
     CK(cudaMalloc(&a, total * 16));
     CK(cudaMalloc(&b, total * 16));
@@ -202,8 +204,17 @@ int main(int argc, char** argv) {
     CK(cudaMemset(b, 0, total * 16));
     double ms = bench([&] { CK(cudaMemcpyAsync(b, a, total * 16, cudaMemcpyDeviceToDevice)); });
     printf("S=%lld memcpy D2D %8.3f ms %7.1f GB/s\n", S, ms, 2.0 * total * 16 / ms / 1e6);
-    struct View { const char* tag; long long outer, N, inner; } views[2] = {{"axis1", S, S, S}, {"axis0", 1, S, S * S}};
+    struct View { const char* tag; long long outer, N, inner; } views[2] = {{"axis1", S, S, S}, {"axis0", 1, S, S * S + pad}};
     for (auto& v : views) {
+        if (quick) {
+            if (v.outer != 1) continue;
+            run_reg<4, 16>(v.tag, a, b, v.outer, v.N, v.inner, 0);
+            run_reg<8, 16>(v.tag, a, b, v.outer, v.N, v.inner, 0);
+            run_reg<16, 16>(v.tag, a, b, v.outer, v.N, v.inner, 0);
+            run_tma<2>(v.tag, a, b, v.outer, v.N, v.inner, 4, 1, 0);
+            run_tma<2>(v.tag, a, b, v.outer, v.N, v.inner, 8, 1, 0);
+            continue;
+        }
         // register path: P x E grid, unconstrained occupancy and 2/1 CTAs per SM via shared memory ballast
         for (int pad : {0, 100 * 1024}) {
             run_reg<2, 8>(v.tag, a, b, v.outer, v.N, v.inner, pad);

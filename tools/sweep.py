@@ -35,11 +35,13 @@ def main():
         pass
     S = args.size
     shape = (S, S, S) if args.shape is None else tuple(int(x) for x in args.shape.split(','))
-    if '-' in args.variants:
-        lo, hi = args.variants.split('-')
-        variants = list(range(int(lo), int(hi) + 1))
-    else:
-        variants = [int(v) for v in args.variants.split(',')]
+    variants = []
+    for part in args.variants.split(','):
+        if '-' in part:
+            lo, hi = part.split('-')
+            variants += list(range(int(lo), int(hi) + 1))
+        else:
+            variants.append(int(part))
     a = B.fftw.aligned(shape, dtype=args.dtype)
     b = B.fftw.aligned(shape, dtype=args.dtype)
     a.tensor.copy_(torch.view_as_complex(torch.rand(shape + (2,), dtype=a.tensor.real.dtype, device='cuda')))
@@ -73,7 +75,7 @@ def main():
                     for _ in range(3):
                         plan()
                 except Exception:
-                    break       # variant not built for this length
+                    continue    # variant not built for this length
                 torch.cuda.synchronize()
                 e0.record(stream)
                 for _ in range(args.reps):
@@ -86,7 +88,7 @@ def main():
                     axis, key[8:], var, 'inplace ' if inplace else 'outplace', ms, gbs, gbs / peak), flush=True)
         _lib.set_option(key, 0)
     _lib.set_option('variant_strict', 0)
-    _lib.set_option('strided_engine', 1)
+    _lib.set_option('strided_engine', 0)
 
 
 if __name__ == '__main__':
