@@ -340,6 +340,9 @@ def run_b200(args):
         except Exception as exc:
             cpu = {"value": None, "unit": "GPoints/s", "error": repr(exc)[:200]}
 
+    modes = sorted(set('p2p put kernel over CUDA-IPC windows' if v is not None else 'pack + NCCL send/recv + unpack'
+                       for v in fft._buffers.peers.values()))
+    transfer_mode = ' / '.join(modes) if modes else ('none (single rank)' if world == 1 else 'pack + NCCL send/recv + unpack')
     if rank == 0:
         grid = [c.Get_size() for c in fft.subcomm]
         line = {
@@ -349,6 +352,7 @@ def run_b200(args):
             "data": "synthetic", "impl": "b200",
             "config": {"workload": workload_name(S), "grid": grid, "local_shape": list(u.shape),
                        "l2": "inputs larger than L2 (%.1f GiB per array per GPU)" % (u.nbytes / 2 ** 30),
+                       "transfer": transfer_mode,
                        "roundtrip_max_err": err},
             "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "gpu_launches": int(launches),

@@ -142,6 +142,24 @@ B2F_API int b2f_transfer_geometry(b2f_transfer t,
 B2F_API int b2f_transfer_pack  (b2f_transfer t, int direction, const void *d_src, void *d_packed, void *stream);
 B2F_API int b2f_transfer_unpack(b2f_transfer t, int direction, const void *d_packed, void *d_dst, void *stream);
 
+/* ---- (2b) the same redistribution over peer memory (NVLink) ---------------
+ * One kernel per transfer: every rank stores the block each peer needs straight
+ * into that peer's array -- no pack, no staging, no unpack.  The destination
+ * arrays ("windows") are cudaMalloc'ed by the library, exported once with CUDA
+ * IPC and mapped by the peers; the 64-byte handles travel through the host side
+ * (as the NCCL unique id does).  Replaces the same Alltoallw (pencil.py:182,200). */
+B2F_API int b2f_malloc(void **d_ptr, size_t bytes);          /* cudaMalloc: IPC-exportable memory */
+B2F_API int b2f_free(void *d_ptr);
+B2F_API int b2f_ipc_export(const void *d_ptr, void *handle64);
+B2F_API int b2f_ipc_open(const void *handle64, void **d_peer);
+B2F_API int b2f_ipc_close(void *d_peer);
+/* direction 0: A -> B, 1: B -> A.  peer_dst[i] = base of the destination array on
+ * group rank i as mapped in THIS process (peer_dst[rank] = the local one).
+ * _put enqueues the kernel only (the caller orders it against the peers);
+ * _exchange_p2p = group barrier, put, group barrier, all on `stream`.          */
+B2F_API int b2f_transfer_put(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
+B2F_API int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,13 @@ SYMBOLS = {
     'b2f_transfer_geometry': (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _i64p]),
     'b2f_transfer_pack': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'b2f_transfer_unpack': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'b2f_malloc': (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    'b2f_free': (C.c_int, [C.c_void_p]),
+    'b2f_ipc_export': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'b2f_ipc_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'b2f_ipc_close': (C.c_int, [C.c_void_p]),
+    'b2f_transfer_put': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    'b2f_transfer_exchange_p2p': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
 }
 
 _lib = None
@@ -205,6 +212,20 @@ class TransferHandle(object):
                                           C.c_void_p(device_ptr(arrayA)), current_stream_ptr()),
               'b2f_transfer_backward')
 
+    def put(self, direction, src, peer_ptrs):
+        """the peer-memory kernel alone (no ordering against the peers)"""
+        from .devarray import device_ptr
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        check(lib().b2f_transfer_put(self._h, int(direction), C.c_void_p(device_ptr(src)), arr,
+                                     current_stream_ptr()), 'b2f_transfer_put')
+
+    def exchange_p2p(self, direction, src, peer_ptrs):
+        """group barrier -> put kernel -> group barrier on the current stream"""
+        from .devarray import device_ptr
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        check(lib().b2f_transfer_exchange_p2p(self._h, int(direction), C.c_void_p(device_ptr(src)), arr,
+                                              current_stream_ptr()), 'b2f_transfer_exchange_p2p')
+
     def pack(self, direction, src, packed):
         from .devarray import device_ptr
         check(lib().b2f_transfer_pack(self._h, int(direction), C.c_void_p(device_ptr(src)),
@@ -225,5 +246,66 @@ class TransferHandle(object):
     def __del__(self):
         try:
             self.destroy()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# peer-memory windows: cudaMalloc'ed by the library, exported / mapped with CUDA IPC
+# ---------------------------------------------------------------------------
+class _RawCuda(object):
+    """__cuda_array_interface__ carrier so that torch can view library memory"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class Window(object):
+    """A byte buffer in HBM that peers of this node can map (b2f_malloc +
+    b2f_ipc_export); ``tensor`` is a uint8 torch view of it."""
+
+    def __init__(self, nbytes):
+        import torch
+        self.nbytes = int(max(nbytes, 16))
+        p = C.c_void_p()
+        check(lib().b2f_malloc(C.byref(p), self.nbytes), 'b2f_malloc')
+        self.ptr = int(p.value)
+        self._carrier = _RawCuda(self.ptr, self.nbytes)
+        self.tensor = torch.as_tensor(self._carrier, device=torch.device('cuda', torch.cuda.current_device()))
+        assert self.tensor.data_ptr() == self.ptr
+        self._peers = []
+
+    def handle(self):
+        buf = C.create_string_buffer(64)
+        check(lib().b2f_ipc_export(C.c_void_p(self.ptr), buf), 'b2f_ipc_export')
+        return bytes(buf.raw)
+
+    def open_peer(self, handle_bytes):
+        buf = C.create_string_buffer(handle_bytes, 64)
+        p = C.c_void_p()
+        check(lib().b2f_ipc_open(buf, C.byref(p)), 'b2f_ipc_open')
+        self._peers.append(int(p.value))
+        return int(p.value)
+
+    def close_peers(self):
+        """unmap the peers' windows (do this on every rank before any rank frees)"""
+        if self._peers:
+            import torch
+            torch.cuda.synchronize()
+            for q in self._peers:
+                lib().b2f_ipc_close(C.c_void_p(q))
+            self._peers = []
+
+    def free(self):
+        if self.ptr:
+            self.close_peers()
+            self.tensor = None
+            lib().b2f_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass

@@ -23,6 +23,7 @@
 #include <vector>
 #include "b200fft.h"
 #include "internal.h"
+#include "transfer_put.h"
 
 namespace b2f {
 
@@ -36,6 +37,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGetVersion) GetVersion = nullptr;
     bool ok = false;
@@ -77,6 +79,7 @@ static void load_nccl() {
     B2F_SYM(Recv, "ncclRecv")
     B2F_SYM(GroupStart, "ncclGroupStart")
     B2F_SYM(GroupEnd, "ncclGroupEnd")
+    B2F_SYM(AllReduce, "ncclAllReduce")
     B2F_SYM(GetErrorString, "ncclGetErrorString")
     B2F_SYM(GetVersion, "ncclGetVersion")
 #undef B2F_SYM
@@ -184,6 +187,53 @@ static int workspace(int slot, size_t bytes, void** out) {
     return B2F_OK;
 }
 
+
+// ---- peer-memory put: the whole redistribution as ONE kernel ------------------
+// Every rank stores the block each peer needs straight into that peer's array
+// (peer pointers are CUDA-IPC mappings of the peers' work buffers, reached over
+// NVLink/NVSwitch), so the pack pass, the staging buffers and the unpack pass of
+// the NCCL formulation disappear: the block is read once from local HBM and
+// written once into its final place.
+//
+// Geometry (direction-neutral: S = source side, D = destination side).  The
+// group-local shape is collapsed to five extents around the two split axes,
+// ax1 < ax2:  (P, e1, M, e2, Q).  The block for peer i has extents
+// (P, b1, M, b2, Q) on both sides and is a set of P*b1*M rows, each b2*Q
+// elements long and contiguous in the source AND in the destination.
+//   source      S[p, o1S + i1, m, o2S + i2, q]     extents (P, e1S, M, e2S, Q)
+//   destination D[p, o1D + i1, m, o2D + i2, q]     extents (P, e1D, M, e2D, Q)
+// All row quantities are kept in units of V bytes (V = widest vector that
+// divides every row length and offset).
+#if defined(__CUDACC__)
+template <class V>
+__global__ void __launch_bounds__(256) put_blocks_kernel(const PutParams prm) {
+    const PutPeer& pr = prm.peer[blockIdx.y];
+    const V* __restrict__ src = reinterpret_cast<const V*>(prm.src);
+    V* __restrict__ dst = reinterpret_cast<V*>(pr.dst);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent units per thread in flight
+    for (; u + 3 * step < pr.units; u += 4 * step) {
+        long long s0, d0, s1, d1, s2, d2, s3, d3;
+        put_locate(prm, pr, u, &s0, &d0);
+        put_locate(prm, pr, u + step, &s1, &d1);
+        put_locate(prm, pr, u + 2 * step, &s2, &d2);
+        put_locate(prm, pr, u + 3 * step, &s3, &d3);
+        const V a = src[s0], b = src[s1], c = src[s2], d = src[s3];
+        dst[d0] = a;
+        dst[d1] = b;
+        dst[d2] = c;
+        dst[d3] = d;
+    }
+    for (; u < pr.units; u += step) {
+        long long s0, d0;
+        put_locate(prm, pr, u, &s0, &d0);
+        dst[d0] = src[s0];
+    }
+    __threadfence_system();   // peer stores are performed before the kernel retires
+}
+#endif
+
 }  // namespace b2f
 
 using namespace b2f;
@@ -191,6 +241,7 @@ using namespace b2f;
 struct b2f_comm_s {
     ncclComm_t comm;
     int nranks, rank;
+    int* d_flag;   // two ints for the stream-ordered group barrier of the peer-memory path
 };
 
 struct b2f_transfer_s {
@@ -228,13 +279,21 @@ int b2f_comm_create(b2f_comm* comm, const void* id128, int nranks, int rank) {
     ncclComm_t c;
     ncclResult_t r = g_nccl.CommInitRank(&c, nranks, id, rank);
     if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitRank");
-    *comm = new b2f_comm_s{c, nranks, rank};
+    int* flag = nullptr;
+    cudaError_t e = cudaMalloc((void**)&flag, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(flag, 0, 2 * sizeof(int));
+    if (e != cudaSuccess) {
+        g_nccl.CommDestroy(c);
+        return cuda_fail(e, "cudaMalloc(barrier flag)");
+    }
+    *comm = new b2f_comm_s{c, nranks, rank, flag};
     return B2F_OK;
 }
 
 int b2f_comm_destroy(b2f_comm comm) {
     if (!comm) return B2F_OK;
     if (g_nccl.ok && comm->comm) g_nccl.CommDestroy(comm->comm);
+    if (comm->d_flag) cudaFree(comm->d_flag);
     delete comm;
     return B2F_OK;
 }
@@ -415,6 +474,119 @@ int b2f_transfer_backward(b2f_transfer t, const void* d_B, void* d_A, void* stre
         return B2F_EINVAL;
     }
     return run_transfer(t, 1, d_B, d_A, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---- peer-memory path -----------------------------------------------------------
+static cudaError_t launch_put(const PutParams& prm, cudaStream_t st) {
+    long long most = 0;
+    for (int k = 0; k < prm.npeers; ++k) most = prm.peer[k].units > most ? prm.peer[k].units : most;
+    if (most == 0) return cudaSuccess;
+    long long blocks = (most + 4 * 256 - 1) / (4 * 256);
+    const long long cap = (long long)option("put_ctas_per_peer", (148LL * 8) / prm.npeers > 148 ? (148LL * 8) / prm.npeers : 148);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)prm.npeers);
+    switch (prm.vec) {
+        case 16: put_blocks_kernel<uint4><<<grid, 256, 0, st>>>(prm); break;
+        case 8: put_blocks_kernel<uint2><<<grid, 256, 0, st>>>(prm); break;
+        case 4: put_blocks_kernel<uint32_t><<<grid, 256, 0, st>>>(prm); break;
+        case 2: put_blocks_kernel<uint16_t><<<grid, 256, 0, st>>>(prm); break;
+        default: put_blocks_kernel<uint8_t><<<grid, 256, 0, st>>>(prm); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+static int build_put(b2f_transfer t, int direction, const void* d_src, void* const* peer_dst, PutParams* prm) {
+    if (t->nranks > B2F_PUT_MAX_PEERS) {
+        set_error("peer-memory transfer supports groups of up to " + std::to_string(B2F_PUT_MAX_PEERS) + " ranks");
+        return B2F_EUNSUPPORTED;
+    }
+    const int axisS = direction == 0 ? t->axisA : t->axisB, axisD = direction == 0 ? t->axisB : t->axisA;
+    if (put_build(prm, t->ndims, t->shape.data(), t->itemsize, axisS, axisD, t->nranks, t->rank, d_src, peer_dst)) {
+        set_error("put_build failed");
+        return B2F_EINVAL;
+    }
+    return B2F_OK;
+}
+
+// stream-ordered barrier over the group: a 1-int all-reduce.  When it completes on
+// this rank's stream every peer has reached it on its own stream, i.e. everything
+// the peers enqueued before it (their kernels reading or writing the windows) is done.
+static int group_barrier(b2f_comm c, cudaStream_t st) {
+    ncclResult_t r = g_nccl.AllReduce(c->d_flag, c->d_flag + 1, 1, ncclInt32, ncclSum, c->comm, st);
+    return r == ncclSuccess ? B2F_OK : nccl_fail(r, "ncclAllReduce(barrier)");
+}
+
+extern "C" {
+
+int b2f_malloc(void** d_ptr, size_t bytes) {
+    if (!d_ptr) return B2F_EINVAL;
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "cudaMalloc");
+}
+
+int b2f_free(void* d_ptr) {
+    cudaError_t e = cudaFree(d_ptr);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "cudaFree");
+}
+
+int b2f_ipc_export(const void* d_ptr, void* handle64) {
+    if (!d_ptr || !handle64) return B2F_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle64, &h, 64);
+    return B2F_OK;
+}
+
+int b2f_ipc_open(const void* handle64, void** d_peer) {
+    if (!handle64 || !d_peer) return B2F_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "cudaIpcOpenMemHandle");
+}
+
+int b2f_ipc_close(void* d_peer) {
+    cudaError_t e = cudaIpcCloseMemHandle(d_peer);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
+int b2f_transfer_put(b2f_transfer t, int direction, const void* d_src, void* const* peer_dst, void* stream) {
+    if (!t || !d_src || !peer_dst || (direction != 0 && direction != 1)) {
+        set_error("b2f_transfer_put: bad arguments");
+        return B2F_EINVAL;
+    }
+    PutParams prm;
+    int rc = build_put(t, direction, d_src, peer_dst, &prm);
+    if (rc) return rc;
+    cudaError_t e = launch_put(prm, (cudaStream_t)stream);
+    return e == cudaSuccess ? B2F_OK : cuda_fail(e, "put kernel");
+}
+
+int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void* d_src, void* const* peer_dst, void* stream) {
+    if (!t || !d_src || !peer_dst || (direction != 0 && direction != 1)) {
+        set_error("b2f_transfer_exchange_p2p: bad arguments");
+        return B2F_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (t->nranks == 1) return b2f_transfer_put(t, direction, d_src, peer_dst, stream);
+    if (!t->comm) {
+        set_error("transfer was created without a communicator");
+        return B2F_EINVAL;
+    }
+    int rc = need_nccl();
+    if (rc) return rc;
+    PutParams prm;
+    if ((rc = build_put(t, direction, d_src, peer_dst, &prm))) return rc;
+    if ((rc = group_barrier(t->comm, st))) return rc;      // the peers are done with their windows
+    cudaError_t e = launch_put(prm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "put kernel");
+    return group_barrier(t->comm, st);                      // every block has landed in my window
 }
 
 }  // extern "C"

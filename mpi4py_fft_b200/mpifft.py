@@ -34,6 +34,84 @@ class _Buffers(object):
         self.spec = {'X': x_spec, 'Y': y_spec}
         self.arr = {}
         self.work = {}
+        self.need = {}          # label -> bytes (max over every use, both directions)
+        self.windows = None     # label -> _lib.Window once the peer-memory path is set up
+        self.peers = {}         # id(Transfer) -> {label: [mapped base pointer per group rank]} | None
+
+    def reserve(self, label, nbytes):
+        self.need[label] = max(self.need.get(label, 0), int(nbytes))
+
+    def setup_windows(self, transfers):
+        """Collective over every transfer group (each rank walks its transfers in
+        plan order): allocate the work buffers as IPC-exportable windows, exchange
+        the handles through the host side and map the peers' windows.  A group in
+        which any rank fails keeps the NCCL path for that transfer."""
+        from . import _lib
+        if self.windows is not None:
+            return
+        self.windows = {}
+        handles = {}
+        ok = True
+        try:
+            for label, nbytes in sorted(self.need.items()):
+                w = _lib.Window(nbytes)
+                self.windows[label] = w
+                handles[label] = w.handle()
+        except Exception as exc:   # e.g. IPC not permitted in this container
+            ok = False
+            handles = {'error': repr(exc)[:200]}
+        opened = {}
+        for t in transfers:
+            comm = t.comm
+            if comm.Get_size() == 1:
+                continue
+            everyone = comm.allgather((ok, handles))
+            me = comm.Get_rank()
+            good = all(e[0] for e in everyone)
+            table = None
+            if good:
+                try:
+                    table = {}
+                    for label, w in self.windows.items():
+                        ptrs = []
+                        for j, (_, hs) in enumerate(everyone):
+                            if j == me:
+                                ptrs.append(w.ptr)
+                            else:
+                                key = hs[label]
+                                if key not in opened:
+                                    opened[key] = w.open_peer(key)
+                                ptrs.append(opened[key])
+                        table[label] = ptrs
+                except Exception:
+                    table = None
+            # the decision must be the same on every rank of the group
+            agreed = all(comm.allgather(table is not None))
+            self.peers[id(t)] = table if agreed else None
+
+    def window_view(self, label, shape, dtype):
+        import torch
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        w = self.windows[label]
+        assert nbytes <= w.nbytes, "work buffer %s smaller than a planned use" % label
+        return DeviceArray(w.tensor[:nbytes].view(torch_dtype(dtype)).view(tuple(shape)))
+
+    def free(self, groups=()):
+        """``groups``: the transfer communicators -- when given (PFFT.destroy is
+        collective, as the reference's) every rank unmaps its peers' windows before
+        any rank releases its own."""
+        if self.windows:
+            for w in self.windows.values():
+                w.close_peers()
+            for comm in groups:
+                if comm.Get_size() > 1:
+                    comm.Barrier()
+            for w in self.windows.values():
+                w.free()
+        self.windows = None
+        self.peers = {}
+        self.work = {}
 
     def endpoint(self, name):
         if name not in self.arr:
@@ -43,6 +121,8 @@ class _Buffers(object):
     def view(self, name, shape, dtype):
         """Typed view of work buffer ``name`` (grown on demand)."""
         import torch
+        if self.windows and name in self.windows:
+            return self.window_view(name, shape, dtype)
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dtype.itemsize
         buf = self.work.get(name)
@@ -72,6 +152,7 @@ class Transform(object):
             ends = ('X', 'Y')
         self._buffers = buffers
         self._ends = ends
+        self._all_transfers = self._transfer   # PFFT replaces this with the forward-order list (collective order)
         self._plan = self._layout()
 
     # -- arrays -------------------------------------------------------------------
@@ -108,12 +189,18 @@ class Transform(object):
         for st in self._xfftn:
             inplace.append(st.input_shape == st.output_shape and st.input_dtype == st.output_dtype)
         trivial = [getattr(t, '__self__', t).comm.Get_size() == 1 for t in self._transfer]
+        # peer-memory transfers store into plan-owned windows only: the caller's
+        # output array is then written by the last stage (out of place), never by
+        # a transfer, so a non-trivial transfer stops the 'OUT' propagation
+        windowed = p2p_enabled() and not all(trivial)
         a = [None] * m
         b = [None] * m
         a[0] = 'IN'
         b[m - 1] = 'OUT'
         i = m - 1
         while i > 0 and inplace[i]:
+            if windowed and not trivial[i - 1]:
+                break
             a[i] = 'OUT'
             if not trivial[i - 1]:
                 break
@@ -136,7 +223,11 @@ class Transform(object):
                     if b[i] == a[i]:   # cannot happen with two buffers, but stay safe
                         toggle ^= 1
                         b[i] = 'W%d' % toggle
-        return dict(a=a, b=b, trivial=trivial)
+        for i, st in enumerate(self._xfftn):
+            for label, shp, dt in ((a[i], st.input_shape, st.input_dtype), (b[i], st.output_shape, st.output_dtype)):
+                if label not in ('IN', 'OUT'):
+                    self._buffers.reserve(label, int(np.prod(shp)) * np.dtype(dt).itemsize)
+        return dict(a=a, b=b, trivial=trivial, windowed=windowed)
 
     # -- execution -------------------------------------------------------------------
     def _resolve(self, label, shape, dtype, src, out):
@@ -168,6 +259,8 @@ class Transform(object):
 
         plan = self._plan
         m = len(self._xfftn)
+        if plan['windowed'] and self._buffers.windows is None:
+            self._buffers.setup_windows([getattr(t, '__self__', t) for t in self._all_transfers])
         if getattr(first, 'destroys_input', False) and plan['a'][0] == 'IN' and input_array is not None \
                 and src is not self.input_array:
             # a multi-axis c2r stage overwrites what it reads: keep the caller's array intact
@@ -184,13 +277,26 @@ class Transform(object):
                 else:
                     nxt = self._xfftn[i + 1]
                     recv = self._resolve(plan['a'][i + 1], nxt.input_shape, nxt.input_dtype, src, out)
-                    self._transfer[i](dst, recv)
+                    tr = getattr(self._transfer[i], '__self__', None)
+                    table = self._buffers.peers.get(id(tr)) if tr is not None else None
+                    label = plan['a'][i + 1]
+                    if table is not None and label in table:
+                        tr.exchange_p2p(0 if self._transfer[i].__name__ == 'forward' else 1, dst, recv, table[label])
+                    else:
+                        self._transfer[i](dst, recv)
                     cur = recv
 
         if output_array is not None and not direct_out:
             _copy_out(out, output_array)
             return output_array
         return out
+
+
+def p2p_enabled():
+    """Peer-memory transfers (one put kernel over NVLink instead of pack -> NCCL ->
+    unpack) are the default on a multi-GPU node; B2F_P2P=0 keeps the NCCL path."""
+    import os
+    return os.environ.get('B2F_P2P', '1') not in ('0', 'false', 'no', '')
 
 
 def _usable(a, shape, dtype):
@@ -354,10 +460,13 @@ class PFFT(object):
         self.backward = Transform([s.backward for s in self.xfftn[::-1]],
                                   [t.backward for t in self.transfer[::-1]],
                                   self.pencil[::-1], self._buffers, ('Y', 'X'))
+        # window set-up is collective: both directions walk the transfers in the same order
+        self.forward._all_transfers = self.backward._all_transfers = [t.forward for t in self.transfer]
 
     def destroy(self):
         if isinstance(self.subcomm, Subcomm):
             self.subcomm.destroy()
+        self._buffers.free([t.comm for t in self.transfer] if self._buffers.peers else ())
         for t in self.transfer:
             t.destroy()
         for s in self.xfftn:

@@ -240,3 +240,23 @@ extern "C" int emu_fft_pow2(int precision, int n, int var, long long outer, long
     if (precision == 8) return emu_dispatch<double>(n, var, strided, prm, outer);
     return emu_dispatch<float>(n, var, strided, prm, outer);
 }
+
+// ---- peer-memory put (transfer_put.h): the kernel's index map replayed on host
+// memory.  peer_dst are host arrays standing in for the peers' windows.
+#include <cstdint>
+#include "../../mpi4py_fft_b200/csrc/transfer_put.h"
+extern "C" int emu_put(int ndims, const long long* shape, int itemsize, int axisS, int axisD, int p, int rank,
+                       const void* src, void* const* peer_dst, int* vec_out) {
+    PutParams prm;
+    if (put_build(&prm, ndims, shape, itemsize, axisS, axisD, p, rank, src, peer_dst)) return -1;
+    if (vec_out) *vec_out = prm.vec;
+    for (int k = 0; k < prm.npeers; ++k) {
+        const PutPeer& pr = prm.peer[k];
+        for (long long u = 0; u < pr.units; ++u) {
+            long long su, du;
+            put_locate(prm, pr, u, &su, &du);
+            std::memcpy(pr.dst + du * prm.vec, prm.src + su * prm.vec, (size_t)prm.vec);
+        }
+    }
+    return 0;
+}

@@ -69,8 +69,9 @@ def main():
     assert np.abs(np.asarray(ub) - g[fft.local_slice(False)]).max() < 1e-12
     torch.cuda.synchronize()
     comm.Barrier()
+    modes = sorted(set('p2p' if v is not None else 'nccl' for v in fft._buffers.peers.values())) or ['nccl']
     if rank == 0:
-        print('MULTI_OK cases=%d world=%d' % (ran, world), flush=True)
+        print('MULTI_OK cases=%d world=%d transfers=%s' % (ran, world, '+'.join(modes)), flush=True)
     import torch.distributed as dist
     dist.destroy_process_group()
 

@@ -298,6 +298,59 @@ def test_pack_unpack_kernels_vs_numpy(B, itemsize_dtype):
             h.destroy()
 
 
+@pytest.mark.parametrize('itemsize_dtype', ['f', 'd', 'F', 'D'])
+def test_put_kernel_is_alltoallw(B, itemsize_dtype):
+    """the peer-memory put kernel, every rank of a group played on one device
+    (the peers' windows are plain local arrays): block i of A along axisA lands in
+    B of rank i at the sender's block of axisB (reference pencil.py:12-29,182-183),
+    and the backward direction is its inverse"""
+    from mpi4py_fft_b200._lib import TransferHandle
+    from mpi4py_fft_b200.devarray import device_ptr
+    from mpi4py_fft_b200.pencil import _blockdist
+    dt = np.dtype(itemsize_dtype)
+    for shape, axisA, axisB, p in (((6, 7, 5), 2, 1, 3), ((9, 4, 3), 1, 0, 2), ((5, 8, 3, 7), 3, 1, 4),
+                                   ((10, 6), 1, 0, 4), ((8, 64, 32), 2, 1, 2), ((8, 32, 64), 1, 0, 4),
+                                   ((33, 40, 24), 0, 2, 8)):
+        g = rand(shape, dt, 11)
+
+        def blocks(axis_split):
+            out = []
+            for r in range(p):
+                n, s0 = _blockdist(shape[axis_split], p, r)
+                sl = [slice(None)] * len(shape)
+                sl[axis_split] = slice(s0, s0 + n)
+                out.append(np.ascontiguousarray(g[tuple(sl)]))
+            return out
+        A, Bx = blocks(axisB), blocks(axisA)
+        handles = []
+        for rank in range(p):
+            class FakeComm(object):
+                ranks = tuple(range(p))
+                _r = rank
+
+                def Get_size(self):
+                    return p
+
+                def Get_rank(self):
+                    return self._r
+            handles.append(TransferHandle(FakeComm(), shape, dt.itemsize, A[rank].shape, axisA, Bx[rank].shape, axisB,
+                                          exchange=False))
+        for direction, src_np, dst_np in ((0, A, Bx), (1, Bx, A)):
+            src = []
+            for r in range(p):
+                a = B.fftw.aligned(src_np[r].shape, dtype=dt)
+                a[...] = src_np[r]
+                src.append(a)
+            dst = [B.fftw.aligned(d.shape, dtype=dt, fill=0) for d in dst_np]
+            ptrs = [device_ptr(d) for d in dst]
+            for r in range(p):
+                handles[r].put(direction, src[r], ptrs)
+            for r in range(p):
+                assert np.array_equal(np.asarray(dst[r]), dst_np[r]), (shape, axisA, axisB, p, direction, r)
+        for h in handles:
+            h.destroy()
+
+
 # ---------------------------------------------------------------------------
 # BASELINE config C2 at full size: properties that do not need a full oracle run
 # ---------------------------------------------------------------------------

@@ -2,6 +2,8 @@
 planning, transfer geometry in Python and in the C ABI) against the reference's
 fixtures -- bit-exact, every rank evaluated as a virtual rank.  CPU only: no
 device memory is touched by planning."""
+import os
+
 import numpy as np
 import pytest
 
@@ -165,9 +167,22 @@ def test_buffer_layout_of_chain():
         assert r.backward._plan['a'][0] == 'IN' and r.backward._plan['b'][-1] == 'OUT'
         assert r.backward._plan['b'][0].startswith('W') and r.backward._plan['a'][2].startswith('W')
     with virtual_world(8, 5):
+        # peer-memory transfers (default): a transfer only ever writes a plan-owned
+        # window, the last stage runs out of place into the caller's array
         f = PFFT(COMM_WORLD, (32, 32, 32), dtype='D')
         lay = f.forward._plan
-        assert lay['trivial'] == [False, False]
+        assert lay['trivial'] == [False, False] and lay['windowed']
+        assert lay['a'] == ['IN', 'W0', 'W1'] and lay['b'] == ['W1', 'W0', 'OUT']
+        assert f.backward._plan['a'] == ['IN', 'W0', 'W1'] and f.backward._plan['b'] == ['W1', 'W0', 'OUT']
+        assert f._buffers.need == {'W0': 16 * 8 * 32 * 16, 'W1': 16 * 8 * 32 * 16}
+        # NCCL path: the last transfer may write the caller's array directly
+        os.environ['B2F_P2P'] = '0'
+        try:
+            f = PFFT(COMM_WORLD, (32, 32, 32), dtype='D')
+        finally:
+            del os.environ['B2F_P2P']
+        lay = f.forward._plan
+        assert not lay['windowed']
         assert lay['a'][0] == 'IN' and lay['b'][0] != lay['a'][1] and lay['a'][2] == 'OUT' and lay['b'][2] == 'OUT'
 
 
