@@ -160,6 +160,21 @@ B2F_API int b2f_ipc_close(void *d_peer);
 B2F_API int b2f_transfer_put(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
 B2F_API int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
 
+/* ---- (1)+(2) fused: the stage's last pass stores into the owners' windows ----
+ * out = scale * T(in), but the last butterfly pass of the stage writes every
+ * point straight into the array of the rank that owns it after transfer `t`
+ * (direction 0: A -> B): the stage output never exists locally and the transfer
+ * costs no kernel of its own -- NVLink traffic overlaps the transform tile by
+ * tile.  Needs the stage's last step to be a Stockham step along the axis `t`
+ * splits (b2f_plan_can_scatter says so); otherwise run b2f_execute followed by
+ * b2f_transfer_exchange_p2p.  `d_work` holds the intermediate of a multi-axis
+ * stage (may be NULL for one axis).  sync != 0 wraps the last step in the two
+ * group barriers, as b2f_transfer_exchange_p2p does.
+ * Replaces libfft.py:412-413 + pencil.py:182-183 in one launch.                */
+B2F_API int b2f_plan_can_scatter(b2f_plan plan, b2f_transfer t, int direction);
+B2F_API int b2f_execute_scatter(b2f_plan plan, const void *d_in, void *d_work, double scale,
+                        b2f_transfer t, int direction, void *const *peer_dst, int sync, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

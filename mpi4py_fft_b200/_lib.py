@@ -47,6 +47,9 @@ SYMBOLS = {
     'b2f_ipc_close': (C.c_int, [C.c_void_p]),
     'b2f_transfer_put': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     'b2f_transfer_exchange_p2p': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    'b2f_plan_can_scatter': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    'b2f_execute_scatter': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                      C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -132,6 +135,18 @@ class Plan(object):
         check(lib().b2f_execute(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), float(scale),
                                 stream if stream is not None else current_stream_ptr()),
               'b2f_execute')
+
+    def can_scatter(self, transfer_handle, direction):
+        """True when the stage's last pass can store into the owners' windows of
+        ``transfer_handle`` (b2f_plan_can_scatter)."""
+        return bool(lib().b2f_plan_can_scatter(self._h, transfer_handle._h, int(direction)))
+
+    def execute_scatter(self, in_ptr, work_ptr, scale, transfer_handle, direction, peer_ptrs, sync=True, stream=None):
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        check(lib().b2f_execute_scatter(self._h, C.c_void_p(in_ptr), C.c_void_p(work_ptr) if work_ptr else None,
+                                        float(scale), transfer_handle._h, int(direction), arr, 1 if sync else 0,
+                                        stream if stream is not None else current_stream_ptr()),
+              'b2f_execute_scatter')
 
     def describe(self):
         buf = C.create_string_buffer(4096)

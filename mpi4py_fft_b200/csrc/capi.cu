@@ -277,9 +277,11 @@ int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int6
     };
     if (k0 == B2F_FORWARD || k0 == B2F_BACKWARD) {
         if (!same_except(-1)) rc = B2F_EINVAL;
-        for (int i = naxes - 1; i >= 0 && rc == B2F_OK; --i)
-            rc = add_step(pl, k0, ax[i], pl->sizes_in, pl->sizes_out, 2, 2,
-                          i == naxes - 1 ? BUF_IN : BUF_OUT, BUF_OUT);
+        // c2c axes commute: the LAST listed axis runs last, because it is the aligned
+        // axis of the pencil (mpifft.py:311,321) -- the one the following transfer
+        // splits -- and only the last step can store into the peers' windows
+        for (int i = 0; i < naxes && rc == B2F_OK; ++i)
+            rc = add_step(pl, k0, ax[i], pl->sizes_in, pl->sizes_out, 2, 2, i == 0 ? BUF_IN : BUF_OUT, BUF_OUT);
     } else if (k0 == B2F_R2C) {
         if (!same_except(last) || sizes_out[last] != sizes_in[last] / 2 + 1) rc = B2F_EINVAL;
         if (rc == B2F_OK) rc = add_step(pl, B2F_R2C, last, pl->sizes_in, pl->sizes_out, 1, 2, BUF_IN, BUF_OUT);
@@ -315,7 +317,30 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
         set_error("b2f_execute: null plan or buffer");
         return B2F_EINVAL;
     }
-    cudaStream_t st = (cudaStream_t)stream;
+    return run_plan(pl, d_in, d_out, scale, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+namespace b2f {
+
+bool plan_scatter_info(b2f_plan pl, int* axis, long long* n, int* precision, const long long** out_shape, int* ndims) {
+    if (!pl || pl->steps.empty()) return false;
+    const Step& s = pl->steps.back();
+    if (s.type != STEP_POW2) return false;
+    *axis = s.axis;
+    *n = s.n_out;
+    *precision = pl->precision;
+    *out_shape = pl->sizes_out.data();
+    *ndims = pl->ndims;
+    return true;
+}
+
+// Runs the steps of a plan.  With `peer` the last step stores into the owners'
+// arrays (fused redistribution) and `before_last(ctx)` is enqueued right before
+// it (the group barrier that says the peers' windows may be overwritten).
+int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStream_t st, const PeerStore* peer_last,
+             int (*before_last)(void*, cudaStream_t), void* ctx) {
     const int variant = (int)option("variant", 0);
     const int variant_c = (int)option("variant_contig", variant);
     const int variant_s = (int)option("variant_strided", variant);
@@ -328,10 +353,16 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
         const void* src = (s.src == BUF_IN) ? d_in : d_out;
         void* dst = (s.dst == BUF_IN) ? const_cast<void*>(d_in) : d_out;
         const double sc = (si + 1 == nsteps) ? scale : 1.0;
+        const PeerStore* peer = (si + 1 == nsteps) ? peer_last : nullptr;
+        if (si + 1 == nsteps && before_last) {
+            const int rc = before_last(ctx, st);
+            if (rc) return rc;
+        }
         cudaError_t e;
         if (s.type == STEP_POW2) {
             FftParams prm;
             memset(&prm, 0, sizeof(prm));
+            if (peer) prm.peer = *peer;
             prm.in = src;
             prm.out = dst;
             prm.scale = sc;
@@ -363,7 +394,7 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
             e = cudaErrorInvalidValue;
             bool done = false;
             if (strided && engine != 1) {
-                TmaStep ts{src, dst, s.outer, s.n_in, s.inner, sc, s.swap ? 1 : 0};
+                TmaStep ts{src, dst, s.outer, s.n_in, s.inner, sc, s.swap ? 1 : 0, peer};
                 auto staged = [&](int v) {
                     return pl->precision == 8 ? launch_tma_f64(n, v, ts, st) : launch_tma_f32(n, v, ts, st);
                 };
@@ -384,6 +415,10 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
                 if (e == cudaErrorInvalidValue && var != 0 && !strict) e = launch(0);   // variant not built for this n
             }
         } else {
+            if (peer) {
+                set_error("fused redistribution needs a power-of-two Stockham step last");
+                return B2F_EUNSUPPORTED;
+            }
             GenericParams g;
             memset(&g, 0, sizeof(g));
             g.in = src;
@@ -404,6 +439,10 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
     }
     return B2F_OK;
 }
+
+}  // namespace b2f
+
+extern "C" {
 
 int b2f_destroy_plan(b2f_plan pl) {
     delete pl;   // tables are cached library-wide

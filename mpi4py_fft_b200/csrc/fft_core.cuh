@@ -175,6 +175,64 @@ inline void build_pass_twiddles(cplx<T>* out) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused redistribution: the last pass of a stage can store straight into the
+// arrays of the ranks that own each part of the transformed axis (peer memory
+// over NVLink), instead of writing the local block and moving it afterwards.
+// It replaces "stage output -> MPI_Alltoallw" of the reference
+// (/root/reference/mpi4py_fft/mpifft.py:70-74 with pencil.py:182-183): the axis
+// just transformed (extent N here) is the one the following transfer splits.
+//
+// Point n of the pencil with outer index o and inner index i goes to owner
+// w = owner(n) of the balanced distribution of N over p ranks, at element
+//     (part * len(w) + n - start(w)) * stride + rest
+// of w's array, where (part, rest) depend on the pencil only:
+//   mode 0 (the axis the destination gathers comes BEFORE the transformed axis;
+//           local block = (P, nD, M, N, Q), destination = (P, ND, M, len(w), Q)):
+//           o = (pp*nD + i1)*M + m ->  part = (pp*ND + sD + i1)*M + m,  rest = i,   stride = Q
+//   mode 1 (it comes AFTER; local block = (P, N, M, nD, Q), destination =
+//           (P, len(w), M, ND, Q)):
+//           i = (m*nD + i2)*Q + qq ->  part = o,  rest = (m*ND + sD + i2)*Q + qq,  stride = M*ND*Q
+// p == 1 with one base pointer reproduces the plain local layout.
+// ---------------------------------------------------------------------------
+#define B2F_MAX_PEERS 16
+struct PeerStore {
+    void* base[B2F_MAX_PEERS];
+    long long stride;
+    long long M, nD, ND, sD, Q;
+    int p;            // owners of the transformed axis (0 = fused store not in use)
+    int q, r;         // N = p*q + r: the first r owners hold q + 1 points
+    int mode;
+
+    B2F_HD void locate(long long o, long long i, long long* part, long long* rest) const {
+        if (mode == 0) {
+            const long long t = o / M, m = o - t * M;
+            const long long pp = t / nD, i1 = t - pp * nD;
+            *part = (pp * ND + sD + i1) * M + m;
+            *rest = i;
+        } else {
+            const long long t = i / Q, qq = i - t * Q;
+            const long long m = t / nD, i2 = t - m * nD;
+            *part = o;
+            *rest = (m * ND + sD + i2) * Q + qq;
+        }
+    }
+    B2F_HD int owner(int n, int* len, int* start) const {
+        const int big = r * (q + 1);
+        int w;
+        if (n < big) {
+            w = n / (q + 1);
+            *len = q + 1;
+            *start = w * (q + 1);
+        } else {
+            w = r + (n - big) / q;
+            *len = q;
+            *start = big + (w - r) * q;
+        }
+        return w;
+    }
+};
+
 // shared-memory index of point i of pencil p inside a CTA tile.
 //   CONTIG : pencils are separate rows, row pitch PITCH, one pad slot every
 //            2^PS points (keeps stride-R writes of pass 0 conflict free)
@@ -347,6 +405,28 @@ struct TileFFT {
                 a.y *= scale;
                 if (swap) { T t = a.x; a.x = a.y; a.y = t; }
                 gout[(long long)n * nstride] = a;
+            }
+        }
+    }
+    // ---- last pass store into the owners' arrays (see PeerStore) ----------------
+    static B2F_HD void store_peer(const C* v, int q, const PeerStore& ps, long long part, long long rest,
+                                  bool valid, bool swap, T scale) {
+        constexpr int R = RAD::get(NPASS - 1);
+        constexpr int NB = E / R;
+        if (!valid) return;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = q + b * TP + r * (N / R);
+                C a = v[b * R + r];
+                a.x *= scale;
+                a.y *= scale;
+                if (swap) { T t = a.x; a.x = a.y; a.y = t; }
+                int len, start;
+                const int w = ps.owner(n, &len, &start);
+                C* dst = reinterpret_cast<C*>(ps.base[w]);
+                dst[(part * len + (n - start)) * ps.stride + rest] = a;
             }
         }
     }

@@ -28,6 +28,7 @@ struct FftParams {
     long long tiles_per_outer;
     double scale;
     int swap;
+    PeerStore peer;          // peer.p > 0: the last pass stores into the owners' arrays (fused redistribution)
 };
 
 #if defined(__CUDACC__)
@@ -50,7 +51,7 @@ struct MidPasses {
 // SWAP is a compile-time constant inside the body so that the re/im exchange
 // of the backward transform costs no register moves around the 16-byte
 // loads/stores (the kernel branches once on prm.swap).
-template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, bool SWAP>
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, bool SWAP, bool PEER>
 __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
     using C = cplx<T>;
@@ -64,6 +65,7 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
     const C* gin;
     C* gout;
     long long in_ns, out_ns;
+    long long po, pi;   // pencil coordinates (outer, inner) for the fused peer store
     bool valid;
     if (STRIDED) {
         const long long bid = blockIdx.x;
@@ -74,6 +76,8 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
         gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
         in_ns = prm.in_nstride;
         out_ns = prm.out_nstride;
+        po = o;
+        pi = i;
     } else {
         const long long gp = (long long)blockIdx.x * P + p;
         valid = gp < prm.npencils;
@@ -81,6 +85,8 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
         gout = reinterpret_cast<C*>(prm.out) + gp * prm.out_ostride;
         in_ns = 1;
         out_ns = 1;
+        po = gp;
+        pi = 0;
     }
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
 
@@ -94,13 +100,26 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
         TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
         TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
     }
-    TF::store_global(v, q, gout, out_ns, valid, SWAP, (T)prm.scale);
+    if constexpr (PEER) {
+        long long part = 0, rest = 0;
+        if (valid) prm.peer.locate(po, pi, &part, &rest);
+        TF::store_peer(v, q, prm.peer, part, rest, valid, SWAP, (T)prm.scale);
+    } else {
+        TF::store_global(v, q, gout, out_ns, valid, SWAP, (T)prm.scale);
+    }
 }
 
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
 __global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftParams prm) {
-    if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true>(prm);
-    else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false>(prm);
+    if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, false>(prm);
+    else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false, false>(prm);
+}
+
+// the same transform with the last pass storing into the owners' arrays (PeerStore)
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_peer_kernel(const FftParams prm) {
+    if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, true>(prm);
+    else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false, true>(prm);
 }
 
 #endif  // __CUDACC__

@@ -35,15 +35,17 @@ static const void* pass_twiddles() {
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
 static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStream_t st) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
-    auto kern = fft_pow2_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>;
+    const bool peer = prm_in.peer.p > 0;
+    auto kern = peer ? fft_pow2_peer_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>
+                     : fft_pow2_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>;
     constexpr size_t smem = TF::NPASS > 1 ? sizeof(cplx<T>) * (size_t)TF::SI::tile_elems : 0;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
+    static bool attr_done[2] = {false, false};   // per instantiation and flavour
+    if (!attr_done[peer]) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        attr_done = true;
+        attr_done[peer] = true;
     }
     FftParams prm = prm_in;
     prm.tw = pass_twiddles<T, RAD>();

@@ -43,6 +43,7 @@ struct TmaParams {
     long long ntiles;
     double scale;
     int swap;
+    PeerStore peer;          // peer.p > 0: fused redistribution (fft_core.cuh)
 };
 
 #if defined(__CUDACC__)
@@ -176,7 +177,7 @@ struct TmaMid {
     }
 };
 
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP>
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP, bool PEER>
 __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const TmaParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
@@ -264,7 +265,13 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         }
         TF::template twiddle_dft<0>(v, q, tw);
         TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT);
-        TF::store_global(v, q, gout, prm.out_nstride, valid, SWAP, (T)prm.scale);
+        if constexpr (PEER) {
+            long long part = 0, rest = 0;
+            if (valid) prm.peer.locate(o, i, &part, &rest);
+            TF::store_peer(v, q, prm.peer, part, rest, valid, SWAP, (T)prm.scale);
+        } else {
+            TF::store_global(v, q, gout, prm.out_nstride, valid, SWAP, (T)prm.scale);
+        }
         if (++s == STAGES) {
             s = 0;
             parity ^= 1;
@@ -275,16 +282,28 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
 template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
 __global__ void __launch_bounds__((N / E) * P, MINB)
 fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true>(&map_in, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false>(&map_in, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, false>(&map_in, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, false>(&map_in, prm);
+}
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB)
+fft_tma_peer_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, true>(&map_in, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, true>(&map_in, prm);
 }
 
 // the same pipeline with the cp.async loader (no descriptor)
 template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
 __global__ void __launch_bounds__((N / E) * P, MINB)
 fft_cpa_kernel(const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true>(nullptr, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false>(nullptr, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, false>(nullptr, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, false>(nullptr, prm);
+}
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB)
+fft_cpa_peer_kernel(const TmaParams prm) {
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, true>(nullptr, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, true>(nullptr, prm);
 }
 
 #endif  // __CUDACC__

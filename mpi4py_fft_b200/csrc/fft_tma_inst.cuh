@@ -38,6 +38,8 @@ static inline void fill_params(TmaParams& prm, const TmaStep& st, int P) {
     prm.ntiles = st.outer * prm.tiles_per_outer;
     prm.scale = st.scale;
     prm.swap = st.swap;
+    if (st.peer) prm.peer = *st.peer;
+    else prm.peer.p = 0;
 }
 
 // cp.async-staged flavour: no descriptor, any layout whose elements are naturally aligned
@@ -45,11 +47,14 @@ template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLI
 static cudaError_t launch_cpa_one(const TmaStep& st, cudaStream_t stream) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
-    auto kern = fft_cpa_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
+    const bool peer = st.peer != nullptr && st.peer->p > 0;
+    auto kern = peer ? fft_cpa_peer_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>
+                     : fft_cpa_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
     constexpr size_t tile_bytes = sizeof(cplx<T>) * (size_t)N * P;
     constexpr size_t smem = STAGES * tile_bytes + EX::bytes;
     static_assert(smem <= 227 * 1024, "tile does not fit shared memory");
-    static int ctas_per_sm = 0;   // per instantiation
+    static int ctas_cache[2] = {0, 0};   // per instantiation and flavour
+    int& ctas_per_sm = ctas_cache[peer];
     if (!ctas_per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -76,11 +81,14 @@ template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLI
 static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
-    auto kern = fft_tma_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
+    const bool peer = st.peer != nullptr && st.peer->p > 0;
+    auto kern = peer ? fft_tma_peer_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>
+                     : fft_tma_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
     constexpr size_t tile_bytes = sizeof(cplx<T>) * (size_t)N * P;
     constexpr size_t smem = STAGES * tile_bytes + EX::bytes;
     static_assert(smem <= 227 * 1024, "tile does not fit shared memory");
-    static int ctas_per_sm = 0;   // per instantiation
+    static int ctas_cache[2] = {0, 0};   // per instantiation and flavour
+    int& ctas_per_sm = ctas_cache[peer];
     if (!ctas_per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -32,10 +32,20 @@ struct TmaStep {
     long long outer, n, inner;
     double scale;
     int swap;
+    const PeerStore* peer;   // non-null: the last pass stores into the owners' arrays
 };
 cudaError_t launch_tma_f64(int n, int var, const TmaStep& st, cudaStream_t stream);
 cudaError_t launch_tma_f32(int n, int var, const TmaStep& st, cudaStream_t stream);
 int sm_count();   // SMs of the current device (cached)
+
+}  // namespace b2f
+struct b2f_plan_s;
+namespace b2f {
+// plan execution with an optional fused peer store in the last step (capi.cu)
+int run_plan(b2f_plan_s* pl, const void* d_in, void* d_out, double scale, cudaStream_t st, const PeerStore* peer_last,
+             int (*before_last)(void*, cudaStream_t), void* ctx);
+// last step of a plan: false unless it is a Stockham step (the only kind that can scatter)
+bool plan_scatter_info(b2f_plan_s* pl, int* axis, long long* n, int* precision, const long long** out_shape, int* ndims);
 
 // generic (any n, any kind) dense-matrix path, dft_generic.cu
 struct GenericParams;

@@ -568,6 +568,69 @@ int b2f_transfer_put(b2f_transfer t, int direction, const void* d_src, void* con
     return e == cudaSuccess ? B2F_OK : cuda_fail(e, "put kernel");
 }
 
+// PeerStore of the stage that feeds transfer `t` in `direction`: the stage's last
+// step transformed the axis the transfer splits (axisS), its output block is the
+// transfer's source array.
+static int build_peer_store(b2f_transfer t, int direction, b2f_plan plan, void* const* peer_dst, PeerStore* ps) {
+    int axis, precision, ndims;
+    long long n;
+    const long long* oshape;
+    if (!plan_scatter_info(plan, &axis, &n, &precision, &oshape, &ndims)) {
+        set_error("fused redistribution: the stage does not end in a Stockham step");
+        return B2F_EUNSUPPORTED;
+    }
+    const int axisS = direction == 0 ? t->axisA : t->axisB, axisD = direction == 0 ? t->axisB : t->axisA;
+    const std::vector<long long>& subS = direction == 0 ? t->subA : t->subB;
+    if (ndims != t->ndims || axis != axisS || t->itemsize != 2 * precision || t->nranks > B2F_MAX_PEERS) {
+        set_error("fused redistribution: the stage's last axis is not the axis the transfer splits");
+        return B2F_EUNSUPPORTED;
+    }
+    for (int i = 0; i < ndims; ++i)
+        if (oshape[i] != subS[i]) {
+            set_error("fused redistribution: stage output shape differs from the transfer's source block");
+            return B2F_EINVAL;
+        }
+    if (peer_store_build(ps, ndims, t->shape.data(), axisS, axisD, t->nranks, t->rank, peer_dst)) {
+        set_error("fused redistribution: bad geometry");
+        return B2F_EINVAL;
+    }
+    return B2F_OK;
+}
+
+static int barrier_hook(void* ctx, cudaStream_t st) { return group_barrier((b2f_comm)ctx, st); }
+
+int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t, int direction,
+                        void* const* peer_dst, int sync, void* stream) {
+    if (!plan || !d_in || !t || !peer_dst || (direction != 0 && direction != 1)) {
+        set_error("b2f_execute_scatter: bad arguments");
+        return B2F_EINVAL;
+    }
+    PeerStore ps;
+    int rc = build_peer_store(t, direction, plan, peer_dst, &ps);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fence = sync && t->nranks > 1;
+    if (fence) {
+        if (!t->comm) {
+            set_error("transfer was created without a communicator");
+            return B2F_EINVAL;
+        }
+        if ((rc = need_nccl())) return rc;
+    }
+    // d_work receives the intermediate of a multi-axis stage; a single-step stage never touches it
+    rc = run_plan(plan, d_in, d_work ? d_work : const_cast<void*>(d_in), scale, st, &ps,
+                  fence ? barrier_hook : nullptr, fence ? (void*)t->comm : nullptr);
+    if (rc) return rc;
+    return fence ? group_barrier(t->comm, st) : B2F_OK;
+}
+
+int b2f_plan_can_scatter(b2f_plan plan, b2f_transfer t, int direction) {
+    if (!plan || !t) return 0;
+    PeerStore ps;
+    void* dummy[B2F_MAX_PEERS] = {};
+    return build_peer_store(t, direction, plan, dummy, &ps) == B2F_OK ? 1 : 0;
+}
+
 int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void* d_src, void* const* peer_dst, void* stream) {
     if (!t || !d_src || !peer_dst || (direction != 0 && direction != 1)) {
         set_error("b2f_transfer_exchange_p2p: bad arguments");

@@ -125,4 +125,39 @@ inline int put_build(PutParams* out, int ndims, const long long* shape, int item
     return 0;
 }
 
+// PeerStore (fft_core.cuh) of a stage whose last step transformed axisS of the
+// group-local `shape` and whose output feeds a transfer axisS -> axisD inside a
+// group of p ranks: the fused form of the same redistribution.
+inline int peer_store_build(PeerStore* ps, int ndims, const long long* shape, int axisS, int axisD, int p, int rank,
+                            void* const* peer_dst) {
+    if (p > B2F_MAX_PEERS || axisS == axisD) return -1;
+    PeerStore z = {};
+    *ps = z;
+    const long long NS = shape[axisS], ND = shape[axisD];
+    long long nD, sD;
+    put_blockdist(ND, p, rank, &nD, &sD);
+    ps->p = p;
+    ps->q = (int)(NS / p);
+    ps->r = (int)(NS % p);
+    ps->nD = nD;
+    ps->ND = ND;
+    ps->sD = sD;
+    for (int i = 0; i < p; ++i) ps->base[i] = peer_dst[i];
+    long long M = 1, Q = 1;
+    if (axisD < axisS) {
+        for (int i = axisD + 1; i < axisS; ++i) M *= shape[i];
+        for (int i = axisS + 1; i < ndims; ++i) Q *= shape[i];
+        ps->mode = 0;
+        ps->stride = Q;
+    } else {
+        for (int i = axisS + 1; i < axisD; ++i) M *= shape[i];
+        for (int i = axisD + 1; i < ndims; ++i) Q *= shape[i];
+        ps->mode = 1;
+        ps->stride = M * ND * Q;
+    }
+    ps->M = M;
+    ps->Q = Q;
+    return 0;
+}
+
 }  // namespace b2f

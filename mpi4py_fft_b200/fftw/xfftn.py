@@ -131,6 +131,14 @@ class FFT(object):
         self.plan().execute(device_ptr(src), device_ptr(dst), scale)
         return dst
 
+    def execute_scatter(self, src, work, scale, transfer_handle, direction, peer_ptrs, sync=True):
+        """The transform with its last pass storing into the owners' windows of the
+        following redistribution (b2f_execute_scatter); ``work`` (may be None for a
+        one-axis stage) holds the intermediate of a multi-axis stage."""
+        assert tuple(src.shape) == self.input_shape and np_dtype_of(src) == self.input_dtype
+        self.plan().execute_scatter(device_ptr(src), device_ptr(work) if work is not None else 0, scale,
+                                    transfer_handle, direction, peer_ptrs, sync)
+
     def __call__(self, input_array=None, output_array=None, implicit=True, normalize=False, **kw):
         """Compute the transform; returns the output array.
 

@@ -91,6 +91,17 @@ class _Stage(object):
         self._planned.execute(src, dst, self._owner.M if normalize else 1.0)
         return dst
 
+    def can_scatter(self, transfer_handle, direction):
+        return self._planned.plan().can_scatter(transfer_handle, direction)
+
+    def run_scatter(self, src, work, normalize, transfer_handle, direction, peer_ptrs):
+        """:meth:`run` fused with the following redistribution: the last pass
+        writes into the peers' windows (used by PFFT on a multi-GPU node)."""
+        if normalize is None:
+            normalize = self._default_normalize
+        self._planned.execute_scatter(src, work, self._owner.M if normalize else 1.0, transfer_handle,
+                                      direction, peer_ptrs)
+
     def __call__(self, input_array=None, output_array=None, **kw):
         normalize = kw.pop('normalize', self._default_normalize)
         src = self._planned._usable(input_array, self.input_shape, self.input_dtype)

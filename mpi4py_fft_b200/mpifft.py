@@ -230,6 +230,20 @@ class Transform(object):
         return dict(a=a, b=b, trivial=trivial, windowed=windowed)
 
     # -- execution -------------------------------------------------------------------
+    def _fused(self, i, st, tr, direction):
+        """can stage i store straight into the windows of transfer i? (decided once;
+        it depends on geometry only, so every rank of the group agrees)"""
+        key = ('fused', i)
+        if key not in self._plan:
+            ok = fused_enabled() and hasattr(st, 'can_scatter')
+            if ok:
+                try:
+                    ok = st.can_scatter(tr._plan(), direction)
+                except Exception:
+                    ok = False
+            self._plan[key] = ok
+        return self._plan[key]
+
     def _resolve(self, label, shape, dtype, src, out):
         if label == 'IN':
             return src
@@ -270,21 +284,27 @@ class Transform(object):
         for i in range(m):
             st = self._xfftn[i]
             dst = self._resolve(plan['b'][i], st.output_shape, st.output_dtype, src, out)
-            st.run(cur, dst, kw.get('normalize'))
-            if i + 1 < m:
-                if plan['trivial'][i]:
-                    cur = dst
-                else:
-                    nxt = self._xfftn[i + 1]
-                    recv = self._resolve(plan['a'][i + 1], nxt.input_shape, nxt.input_dtype, src, out)
-                    tr = getattr(self._transfer[i], '__self__', None)
-                    table = self._buffers.peers.get(id(tr)) if tr is not None else None
-                    label = plan['a'][i + 1]
-                    if table is not None and label in table:
-                        tr.exchange_p2p(0 if self._transfer[i].__name__ == 'forward' else 1, dst, recv, table[label])
+            if i + 1 < m and not plan['trivial'][i]:
+                nxt = self._xfftn[i + 1]
+                recv = self._resolve(plan['a'][i + 1], nxt.input_shape, nxt.input_dtype, src, out)
+                tr = getattr(self._transfer[i], '__self__', None)
+                table = self._buffers.peers.get(id(tr)) if tr is not None else None
+                label = plan['a'][i + 1]
+                direction = 0 if self._transfer[i].__name__ == 'forward' else 1
+                if table is not None and label in table:
+                    if self._fused(i, st, tr, direction):
+                        # one launch: the stage's last pass stores into the owners' windows
+                        st.run_scatter(cur, dst, kw.get('normalize'), tr._plan(), direction, table[label])
                     else:
-                        self._transfer[i](dst, recv)
-                    cur = recv
+                        st.run(cur, dst, kw.get('normalize'))
+                        tr.exchange_p2p(direction, dst, recv, table[label])
+                else:
+                    st.run(cur, dst, kw.get('normalize'))
+                    self._transfer[i](dst, recv)
+                cur = recv
+            else:
+                st.run(cur, dst, kw.get('normalize'))
+                cur = dst
 
         if output_array is not None and not direct_out:
             _copy_out(out, output_array)
@@ -297,6 +317,12 @@ def p2p_enabled():
     unpack) are the default on a multi-GPU node; B2F_P2P=0 keeps the NCCL path."""
     import os
     return os.environ.get('B2F_P2P', '1') not in ('0', 'false', 'no', '')
+
+
+def fused_enabled():
+    """Stage + redistribution in one kernel (B2F_FUSED=0: stage, then put kernel)."""
+    import os
+    return os.environ.get('B2F_FUSED', '1') not in ('0', 'false', 'no', '')
 
 
 def _usable(a, shape, dtype):

@@ -103,6 +103,9 @@ def emu():
                                  ctypes.c_double, ctypes.c_int]
     lib.emu_fft_tma.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong,
                                 ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+    lib.emu_fft_scatter.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_void_p), ctypes.c_double, ctypes.c_int]
     lib.emu_put.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                             ctypes.POINTER(ctypes.c_int)]

@@ -105,8 +105,22 @@ static int emu_one(const FftParams& prm_in, long long outer) {
         // running in == out from the python side)
         for (int tid = 0; tid < TF::THREADS; ++tid) {
             C* v = &regs[(size_t)tid * E];
-            TF::store_global(v, TF::slot_of(tid), loc[tid].gout, loc[tid].out_ns, loc[tid].valid, swap,
-                             (T)prm.scale);
+            if (prm.peer.p > 0) {
+                // the kernel's PEER flavour: pencil coordinates -> (part, rest), then store_peer
+                long long po, pi, part = 0, rest = 0;
+                if (STRIDED) {
+                    po = bid / prm.tiles_per_outer;
+                    pi = (bid - po * prm.tiles_per_outer) * P + TF::pencil_of(tid);
+                } else {
+                    po = bid * P + TF::pencil_of(tid);
+                    pi = 0;
+                }
+                if (loc[tid].valid) prm.peer.locate(po, pi, &part, &rest);
+                TF::store_peer(v, TF::slot_of(tid), prm.peer, part, rest, loc[tid].valid, swap, (T)prm.scale);
+            } else {
+                TF::store_global(v, TF::slot_of(tid), loc[tid].gout, loc[tid].out_ns, loc[tid].valid, swap,
+                                 (T)prm.scale);
+            }
         }
     }
     return 0;
@@ -185,8 +199,15 @@ static int emu_tma_one(const FftParams& prm, long long outer) {
         EmuTmaMid<TF, EX, 1>::run(regs, xbuf.data(), twv.data(), SPLIT);
         for (int tid = 0; tid < TF::THREADS; ++tid) {
             const long long i = i0 + TF::pencil_of(tid);
-            TF::store_global(&regs[(size_t)tid * E], TF::slot_of(tid), gout + o * prm.out_ostride + i, prm.out_nstride,
-                             i < prm.inner, swap, (T)prm.scale);
+            if (prm.peer.p > 0) {
+                long long part = 0, rest = 0;
+                if (i < prm.inner) prm.peer.locate(o, i, &part, &rest);
+                TF::store_peer(&regs[(size_t)tid * E], TF::slot_of(tid), prm.peer, part, rest, i < prm.inner, swap,
+                               (T)prm.scale);
+            } else {
+                TF::store_global(&regs[(size_t)tid * E], TF::slot_of(tid), gout + o * prm.out_ostride + i,
+                                 prm.out_nstride, i < prm.inner, swap, (T)prm.scale);
+            }
         }
     }
     return 0;
@@ -259,4 +280,38 @@ extern "C" int emu_put(int ndims, const long long* shape, int itemsize, int axis
         }
     }
     return 0;
+}
+
+// ---- fused redistribution: FFT along axisS of this rank's block, last pass
+// storing into the owners' arrays (PeerStore).  shape = group-local shape.
+extern "C" int emu_fft_scatter(int precision, int ndims, const long long* shape, int axisS, int axisD, int p, int rank,
+                               int var, int staged, const void* in, void* const* peer_dst, double scale, int swap) {
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    if (peer_store_build(&prm.peer, ndims, shape, axisS, axisD, p, rank, peer_dst)) return -2;
+    long long nD, sD;
+    put_blockdist(shape[axisD], p, rank, &nD, &sD);
+    long long outer = 1, inner = 1;
+    for (int i = 0; i < axisS; ++i) outer *= (i == axisD ? nD : shape[i]);
+    for (int i = axisS + 1; i < ndims; ++i) inner *= (i == axisD ? nD : shape[i]);
+    const int n = (int)shape[axisS];
+    prm.in = in;
+    prm.out = nullptr;
+    prm.scale = scale;
+    prm.swap = swap;
+    const bool strided = inner > 1;
+    if (strided) {
+        prm.in_ostride = prm.out_ostride = (long long)n * inner;
+        prm.in_nstride = prm.out_nstride = inner;
+        prm.inner = inner;
+    } else {
+        prm.in_ostride = prm.out_ostride = n;
+        prm.npencils = outer;
+    }
+    if (staged) {
+        if (!strided) return -3;
+        return precision == 8 ? emu_tma_dispatch<double>(n, var, prm, outer) : emu_tma_dispatch<float>(n, var, prm, outer);
+    }
+    if (precision == 8) return emu_dispatch<double>(n, var, strided, prm, outer);
+    return emu_dispatch<float>(n, var, strided, prm, outer);
 }

@@ -351,6 +351,68 @@ def test_put_kernel_is_alltoallw(B, itemsize_dtype):
             h.destroy()
 
 
+@pytest.mark.parametrize('dtype', ['D', 'F'])
+def test_fused_stage_and_transfer_kernels(B, dtype):
+    """b2f_execute_scatter, every rank of a group played on one device: FFT along
+    the split axis with the last pass storing into the owners' arrays == numpy FFT
+    followed by the reference's Alltoallw (mpifft.py:70-74, pencil.py:182-183);
+    covers the contiguous, register-strided and staged (TMA / cp.async) kernels,
+    both PeerStore modes, uneven splits and a two-axis stage"""
+    from mpi4py_fft_b200._lib import TransferHandle, Plan
+    from mpi4py_fft_b200.devarray import device_ptr
+    from mpi4py_fft_b200.pencil import _blockdist
+    dt = np.dtype(dtype)
+    prec = 8 if dtype == 'D' else 4
+    tol = 1e-12 if dtype == 'D' else 1e-5
+    cases = [((6, 5, 64), (2,), 1, 2), ((6, 5, 64), (2,), 0, 3), ((3, 64, 10), (1,), 0, 2), ((3, 64, 10), (1,), 2, 2),
+             ((64, 7, 6), (0,), 2, 4), ((2, 9, 128, 5, 3), (2,), 1, 4), ((4, 256, 48), (1,), 0, 2),
+             ((512, 6, 40), (0,), 2, 3), ((8, 32, 1024), (2,), 1, 4), ((16, 1024, 24), (1,), 0, 4),
+             ((6, 16, 64), (1, 2), 0, 2)]
+    for shape, axes, axD, p in cases:
+        axS = axes[-1]
+        g = rand(shape, dt, 21)
+
+        def blocks(arr, axis):
+            out = []
+            for r in range(p):
+                n, s0 = _blockdist(shape[axis], p, r)
+                sl = [slice(None)] * len(shape)
+                sl[axis] = slice(s0, s0 + n)
+                out.append(np.ascontiguousarray(arr[tuple(sl)]))
+            return out
+        for kind in (-1, 1):
+            g64 = g.astype(np.complex128)
+            full = np.fft.fftn(g64, axes=axes) if kind == -1 else np.fft.ifftn(g64, axes=axes) * np.prod([shape[a] for a in axes])
+            expect = blocks(full, axS)
+            src_np = blocks(g, axD)
+            dst = [B.fftw.aligned(e.shape, dtype=dt, fill=0) for e in expect]
+            ptrs = [device_ptr(d) for d in dst]
+            for r in range(p):
+                class FakeComm(object):
+                    ranks = tuple(range(p))
+                    _r = r
+
+                    def Get_size(self):
+                        return p
+
+                    def Get_rank(self):
+                        return self._r
+                # transfer A -> B with axisA = axS: A blocks are split along axD, B blocks along axS
+                h = TransferHandle(FakeComm(), shape, dt.itemsize, src_np[r].shape, axS, expect[r].shape, axD,
+                                   exchange=False)
+                plan = Plan(src_np[r].shape, src_np[r].shape, axes, [kind] * len(axes), prec)
+                assert plan.can_scatter(h, 0)
+                a = B.fftw.aligned(src_np[r].shape, dtype=dt)
+                a[...] = src_np[r]
+                work = B.fftw.aligned(src_np[r].shape, dtype=dt)
+                plan.execute_scatter(device_ptr(a), device_ptr(work), 1.0, h, 0, ptrs, sync=False)
+                plan.destroy()
+                h.destroy()
+            for r in range(p):
+                err = np.abs(np.asarray(dst[r]) - expect[r]).max() / np.abs(full).max()
+                assert err < tol, (shape, axes, axD, p, kind, r, err)
+
+
 # ---------------------------------------------------------------------------
 # BASELINE config C2 at full size: properties that do not need a full oracle run
 # ---------------------------------------------------------------------------
