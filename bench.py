@@ -363,6 +363,8 @@ def run_b200(args):
             "gpu_launches": int(launches),
         }
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    fft.destroy()          # collective: unmap the peers' windows, then release the own ones
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -276,12 +276,32 @@ class _RawCuda(object):
                                          'version': 3, 'strides': None}
 
 
+_live_windows = None
+
+
+def _close_windows_at_exit():
+    """unmap peer windows and release the own ones while the CUDA context is still
+    alive (interpreter shutdown order is otherwise arbitrary)"""
+    for w in list(_live_windows or ()):
+        try:
+            w.free()
+        except Exception:
+            pass
+
+
 class Window(object):
     """A byte buffer in HBM that peers of this node can map (b2f_malloc +
     b2f_ipc_export); ``tensor`` is a uint8 torch view of it."""
 
     def __init__(self, nbytes):
         import torch
+        global _live_windows
+        if _live_windows is None:
+            import atexit
+            import weakref
+            _live_windows = weakref.WeakSet()
+            atexit.register(_close_windows_at_exit)
+        _live_windows.add(self)
         self.nbytes = int(max(nbytes, 16))
         p = C.c_void_p()
         check(lib().b2f_malloc(C.byref(p), self.nbytes), 'b2f_malloc')

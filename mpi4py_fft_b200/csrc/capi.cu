@@ -122,7 +122,7 @@ const double* generic_matrix(int kind, long long n, int* rows, int* cols) {
 }
 
 // ---- plan ------------------------------------------------------------------
-enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1 };
+enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1, STEP_REAL = 2 };
 enum Buf { BUF_IN = 0, BUF_OUT = 1 };
 
 struct Step {
@@ -199,6 +199,14 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_pow2(n) && n <= B2F_POW2_MAX_N) {
         s.type = STEP_POW2;
         s.swap = (kind == B2F_BACKWARD);
+    } else if ((kind == B2F_R2C || kind == B2F_C2R) && is_pow2(n) && n >= 4 && n <= 2 * B2F_POW2_MAX_N &&
+               option("real_engine", 0) != 1) {
+        // even-length real transform = n/2-point complex Stockham + split/merge pass
+        s.type = STEP_REAL;
+        if ((kind == B2F_R2C ? s.n_out : s.n_in) != n / 2 + 1) {
+            set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
+            return B2F_EINVAL;
+        }
     } else {
         if (n > B2F_GENERIC_MAX_N) {
             set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
@@ -414,6 +422,32 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 e = launch(var);
                 if (e == cudaErrorInvalidValue && var != 0 && !strict) e = launch(0);   // variant not built for this n
             }
+        } else if (s.type == STEP_REAL) {
+            if (peer) {
+                set_error("fused redistribution needs a power-of-two c2c Stockham step last");
+                return B2F_EUNSUPPORTED;
+            }
+            FftParams prm;
+            memset(&prm, 0, sizeof(prm));
+            prm.in = src;
+            prm.out = dst;
+            prm.scale = sc;
+            const bool strided = s.inner > 1;
+            const int mode = s.kind == B2F_R2C ? 1 : 2;
+            const long long nreal = mode == 1 ? s.n_in : s.n_out, nc = nreal / 2;
+            if (strided) {
+                prm.in_ostride = s.n_in * s.inner;
+                prm.out_ostride = s.n_out * s.inner;
+                prm.in_nstride = prm.out_nstride = s.inner;
+                prm.inner = s.inner;
+            } else {
+                // rows in complex units: 2N reals = N complex on the real side, N+1 on the spectral side
+                prm.in_ostride = mode == 1 ? nc : s.n_in;
+                prm.out_ostride = mode == 1 ? s.n_out : nc;
+                prm.npencils = s.outer;
+            }
+            e = pl->precision == 8 ? launch_real_f64((int)nc, mode, strided, prm, s.outer, st)
+                                   : launch_real_f32((int)nc, mode, strided, prm, s.outer, st);
         } else {
             if (peer) {
                 set_error("fused redistribution needs a power-of-two Stockham step last");
@@ -455,7 +489,8 @@ int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
     for (const Step& st : pl->steps) {
         char line[256];
         snprintf(line, sizeof(line), "%s kind=%d axis=%d n_in=%lld n_out=%lld outer=%lld inner=%lld %s->%s\n",
-                 st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig") : "dense-matrix",
+                 st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig")
+                 : st.type == STEP_REAL ? (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig") : "dense-matrix",
                  st.kind, st.axis, st.n_in, st.n_out, st.outer, st.inner,
                  st.src == BUF_IN ? "in" : "out", st.dst == BUF_IN ? "in" : "out");
         s += line;

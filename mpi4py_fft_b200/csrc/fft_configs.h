@@ -125,6 +125,38 @@
     X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
+// real transforms (r2c / c2r of even length 2N through the N-point schedule,
+// fft_pow2.cuh fft_real_kernel):  X(N, E, P, PS, MINB, radices...), one row per N
+#define B2F_REAL_CONTIG(X)               \
+    X(2, 2, 128, 30, 1, 2)               \
+    X(4, 4, 128, 30, 1, 4)               \
+    X(8, 8, 64, 30, 1, 8)                \
+    X(16, 16, 32, 30, 1, 16)             \
+    X(32, 8, 32, 3, 1, 8, 4)             \
+    X(64, 8, 16, 3, 1, 8, 8)             \
+    X(128, 16, 16, 4, 1, 16, 8)          \
+    X(256, 16, 8, 4, 1, 16, 16)          \
+    X(512, 16, 4, 3, 1, 8, 8, 8)         \
+    X(1024, 16, 2, 4, 1, 16, 8, 8)       \
+    X(2048, 16, 2, 4, 1, 16, 16, 8)      \
+    X(4096, 16, 1, 4, 1, 16, 16, 16)     \
+    X(8192, 16, 1, 4, 1, 16, 8, 8, 8)
+
+#define B2F_REAL_STRIDED(X)              \
+    X(2, 2, 128, 30, 1, 2)               \
+    X(4, 4, 128, 30, 1, 4)               \
+    X(8, 8, 64, 30, 1, 8)                \
+    X(16, 16, 32, 30, 1, 16)             \
+    X(32, 8, 32, 30, 1, 8, 4)            \
+    X(64, 8, 16, 30, 1, 8, 8)            \
+    X(128, 16, 16, 30, 1, 16, 8)         \
+    X(256, 16, 8, 30, 1, 16, 16)         \
+    X(512, 16, 8, 30, 1, 8, 8, 8)        \
+    X(1024, 16, 8, 30, 1, 16, 8, 8)      \
+    X(2048, 16, 2, 4, 1, 16, 16, 8)      \
+    X(4096, 16, 2, 4, 1, 16, 16, 16)     \
+    X(8192, 16, 1, 4, 1, 16, 8, 8, 8)
+
 #define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X)
 #define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X)
 

@@ -175,6 +175,18 @@ inline void build_pass_twiddles(cplx<T>* out) {
     }
 }
 
+// host: w[k] = exp(-2 pi i k / (2N)), k = 0..N-1, the split/merge twiddles of the
+// real transforms of length 2N (long double angles)
+template <class T>
+inline void build_real_twiddles(cplx<T>* out, int N) {
+    const long double PI = 3.14159265358979323846264338327950288L;
+    for (int k = 0; k < N; ++k) {
+        const long double a = PI * (long double)k / (long double)N;
+        out[k].x = (T)cosl(a);
+        out[k].y = (T)(-sinl(a));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Fused redistribution: the last pass of a stage can store straight into the
 // arrays of the ranks that own each part of the transformed axis (peer memory
@@ -427,6 +439,61 @@ struct TileFFT {
                 const int w = ps.owner(n, &len, &start);
                 C* dst = reinterpret_cast<C*>(ps.base[w]);
                 dst[(part * len + (n - start)) * ps.stride + rest] = a;
+            }
+        }
+    }
+    // ---- real transforms: 2N reals <-> N+1 complex through the N-point complex
+    // FFT of the packed pencil z[j] = x[2j] + i x[2j+1]  (replaces
+    // fftw_plan_guru_dft_r2c / _c2r, /root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:57-67).
+    // w[k] = exp(-2 pi i k / 2N), k < N.  X[N] lives in the extra slot tile_elems + p.
+    //
+    // r2c: with Z the transform of z (natural order in shared memory),
+    //   X[k] = (Z[k] + conj Z[N-k])/2 - i w^k (Z[k] - conj Z[N-k])/2,   X[N] = Re Z[0] - Im Z[0]
+    static B2F_HD void r2c_post(int p, int q, const C* smem, const C* __restrict__ w, C* __restrict__ gout,
+                                long long out_ns, bool valid, T scale) {
+        if (!valid) return;
+        const T h = (T)0.5 * scale;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = q + e * TP;
+            const C a = smem[SI::at(p, k)];
+            C b = smem[SI::at(p, (N - k) & (N - 1))];
+            b.y = -b.y;
+            const C sm = a + b, d = a - b;
+            const C t = cmul(w[k], d);
+            C x = {(sm.x + t.y) * h, (sm.y - t.x) * h};
+            gout[(long long)k * out_ns] = x;
+            if (k == 0) {
+                C xn = {(a.x - a.y) * scale, (T)0};
+                gout[(long long)N * out_ns] = xn;
+            }
+        }
+    }
+
+    // c2r: the pass-0 inputs  Z'[n] = (X[n] + conj X[N-n]) + i conj(w^n) (X[n] - conj X[N-n])
+    // (twice the packed spectrum, so that the unnormalised result is FFTW's), already
+    // re/im-swapped for the forward-kernel-as-backward trick.  The imaginary parts of
+    // X[0] and X[N] are ignored, as FFTW does.
+    static B2F_HD void c2r_pre(C* v, int p, int q, const C* smem, const C* __restrict__ w) {
+        constexpr int R = RAD::get(0);
+        constexpr int NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = q + b * TP + r * (N / R);
+                C a = smem[SI::at(p, n)];
+                C c = (n == 0) ? smem[SI::tile_elems + p] : smem[SI::at(p, N - n)];
+                if (n == 0) {
+                    a.y = (T)0;
+                    c.y = (T)0;
+                }
+                c.y = -c.y;
+                const C sm = a + c, d = a - c;
+                C wc = w[n];
+                wc.y = -wc.y;
+                const C t = cmul(wc, d);
+                v[b * R + r] = {sm.y + t.x, sm.x - t.y};   // (re, im) = (sm.x - t.y, sm.y + t.x), swapped
             }
         }
     }

@@ -29,6 +29,7 @@ struct FftParams {
     double scale;
     int swap;
     PeerStore peer;          // peer.p > 0: the last pass stores into the owners' arrays (fused redistribution)
+    const void* rtw;         // real transforms: exp(-2 pi i k / 2N), k < N
 };
 
 #if defined(__CUDACC__)
@@ -120,6 +121,126 @@ template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MIN
 __global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_peer_kernel(const FftParams prm) {
     if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, true>(prm);
     else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false, true>(prm);
+}
+
+
+// ---------------------------------------------------------------------------
+// Real transforms of even length 2N on the same tile machinery (MODE 1 = r2c,
+// 2 = c2r): the pencil is packed into N complex points, transformed by the
+// N-point schedule, and split / merged through shared memory (TileFFT::r2c_post,
+// c2r_pre).  Strides in FftParams are in elements of the respective array:
+//   r2c: in real (outer, 2N, inner), out complex (outer, N+1, inner)
+//   c2r: in complex (outer, N+1, inner), out real (outer, 2N, inner)
+// ---------------------------------------------------------------------------
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MODE>
+__device__ __forceinline__ void fft_real_body(const FftParams& prm) {
+    using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
+    using C = cplx<T>;
+    extern __shared__ __align__(16) unsigned char b2f_smem_raw[];
+    C* smem = reinterpret_cast<C*>(b2f_smem_raw);
+    const int tid = threadIdx.x;
+    const int p = TF::pencil_of(tid);
+    const int q = TF::slot_of(tid);
+    long long o, i;
+    bool valid;
+    if (STRIDED) {
+        const long long bid = blockIdx.x;
+        o = bid / prm.tiles_per_outer;
+        i = (bid - o * prm.tiles_per_outer) * P + p;
+        valid = i < prm.inner;
+    } else {
+        o = (long long)blockIdx.x * P + p;
+        i = 0;
+        valid = o < prm.npencils;
+    }
+    const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
+    const C* __restrict__ rtw = reinterpret_cast<const C*>(prm.rtw);
+    const long long in_ns = STRIDED ? prm.in_nstride : 1, out_ns = STRIDED ? prm.out_nstride : 1;
+    C v[E];
+    if constexpr (MODE == 1) {
+        constexpr int R0 = RAD::get(0);
+        if (STRIDED) {
+            const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+#pragma unroll
+            for (int b = 0; b < E / R0; ++b)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+                    const int n = q + b * TF::TP + r * (N / R0);
+                    C a = {(T)0, (T)0};
+                    if (valid) {
+                        a.x = gin[(long long)(2 * n) * in_ns];
+                        a.y = gin[(long long)(2 * n + 1) * in_ns];
+                    }
+                    v[b * R0 + r] = a;
+                }
+        } else {
+            const C* gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride;
+            TF::load_global(v, q, gin, 1, valid, false);
+        }
+    } else {
+        // c2r: the half spectrum goes to shared memory first (X[N] in the extra slot)
+        const C* gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = q + e * TF::TP;
+            C a = {(T)0, (T)0};
+            if (valid) a = gin[(long long)k * in_ns];
+            smem[TF::SI::at(p, k)] = a;
+        }
+        if (q == 0) {
+            C a = {(T)0, (T)0};
+            if (valid) a = gin[(long long)N * in_ns];
+            smem[TF::SI::tile_elems + p] = a;
+        }
+        __syncthreads();
+        TF::c2r_pre(v, p, q, smem, rtw);
+        __syncthreads();   // every thread has its inputs: the tile may be overwritten
+    }
+    TF::template twiddle_dft<0>(v, q, tw);
+    if constexpr (TF::NPASS > 1) {
+        TF::template store_shared<0>(v, p, q, smem);
+        __syncthreads();
+        MidPasses<TF, 1>::run(v, p, q, smem, tw);
+        TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
+        TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
+    }
+    if constexpr (MODE == 1) {
+        // Z in natural order -> shared memory -> split into the half spectrum
+        if constexpr (TF::NPASS > 1) __syncthreads();   // the last pass has read the tile
+        constexpr int RL = RAD::get(TF::NPASS - 1);
+#pragma unroll
+        for (int b = 0; b < E / RL; ++b)
+#pragma unroll
+            for (int r = 0; r < RL; ++r) smem[TF::SI::at(p, q + b * TF::TP + r * (N / RL))] = v[b * RL + r];
+        __syncthreads();
+        C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
+        TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale);
+    } else {
+        if (STRIDED) {
+            if (valid) {
+                T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                constexpr int RL = RAD::get(TF::NPASS - 1);
+                const T sc = (T)prm.scale;
+#pragma unroll
+                for (int b = 0; b < E / RL; ++b)
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) {
+                        const int n = q + b * TF::TP + r * (N / RL);
+                        // swapped back: x[2n] = im part of the forward result, x[2n+1] = re part
+                        gout[(long long)(2 * n) * out_ns] = v[b * RL + r].y * sc;
+                        gout[(long long)(2 * n + 1) * out_ns] = v[b * RL + r].x * sc;
+                    }
+            }
+        } else {
+            C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride;
+            TF::store_global(v, q, gout, 1, valid, true, (T)prm.scale);
+        }
+    }
+}
+
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB, int MODE>
+__global__ void __launch_bounds__((N / E) * P, MINB) fft_real_kernel(const FftParams prm) {
+    fft_real_body<T, N, E, RAD, P, STRIDED, PS, MODE>(prm);
 }
 
 #endif  // __CUDACC__

@@ -64,6 +64,70 @@ static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStre
     return cudaGetLastError();
 }
 
+// split / merge twiddles of the real transforms, one table per (T, N) and device
+template <class T>
+static const void* real_twiddles(int N) {
+    static std::mutex mu;
+    static const void* cache[64][16] = {};
+    int dev = 0, lg = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    while ((1 << lg) < N) ++lg;
+    std::lock_guard<std::mutex> lk(mu);
+    const void*& slot = cache[dev & 63][lg & 15];
+    if (!slot) {
+        std::vector<cplx<T>> h((size_t)N);
+        build_real_twiddles<T>(h.data(), N);
+        void* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(cplx<T>)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        slot = d;
+    }
+    return slot;
+}
+
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB, int MODE>
+static cudaError_t launch_real_one(const FftParams& prm_in, long long outer, cudaStream_t st) {
+    using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
+    auto kern = fft_real_kernel<T, N, E, RAD, P, STRIDED, PS, MINB, MODE>;
+    constexpr size_t smem = sizeof(cplx<T>) * ((size_t)TF::SI::tile_elems + P);
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        attr_done = true;
+    }
+    FftParams prm = prm_in;
+    prm.tw = pass_twiddles<T, RAD>();
+    prm.rtw = real_twiddles<T>(N);
+    if (!prm.tw || !prm.rtw) return cudaErrorMemoryAllocation;
+    long long grid;
+    if (STRIDED) {
+        prm.tiles_per_outer = (prm.inner + P - 1) / P;
+        grid = outer * prm.tiles_per_outer;
+    } else {
+        grid = (prm.npencils + P - 1) / P;
+    }
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+    kern<<<(unsigned)grid, TF::THREADS, smem, st>>>(prm);
+    count_launch();
+    return cudaGetLastError();
+}
+
+#define B2F_INST_REAL_CONTIG(N, E, P, PS, MINB, ...)                                                       \
+    if (n == N) {                                                                                          \
+        if (mode == 1) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 1>(prm, outer, st); \
+        return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 2>(prm, outer, st);      \
+    }
+#define B2F_INST_REAL_STRIDED(N, E, P, PS, MINB, ...)                                                      \
+    if (n == N) {                                                                                          \
+        if (mode == 1)                                                                                     \
+            return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 1>(prm, outer, st); \
+        return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 2>(prm, outer, st);     \
+    }
+
 // strided tiles are sized in bytes: a float tile takes twice the pencils of a
 // double tile, so that a row of the tile is the same contiguous run in HBM
 template <class T> struct StridedScale { static constexpr int value = (int)(sizeof(double) / sizeof(T)); };

@@ -102,9 +102,14 @@ class _Buffers(object):
         collective, as the reference's) every rank unmaps its peers' windows before
         any rank releases its own."""
         if self.windows:
+            import torch
+            torch.cuda.synchronize()
+            for comm in groups:               # nobody is still storing into a window
+                if comm.Get_size() > 1:
+                    comm.Barrier()
             for w in self.windows.values():
                 w.close_peers()
-            for comm in groups:
+            for comm in groups:               # every mapping is gone before any owner frees
                 if comm.Get_size() > 1:
                     comm.Barrier()
             for w in self.windows.values():

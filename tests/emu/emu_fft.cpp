@@ -315,3 +315,177 @@ extern "C" int emu_fft_scatter(int precision, int ndims, const long long* shape,
     if (precision == 8) return emu_dispatch<double>(n, var, strided, prm, outer);
     return emu_dispatch<float>(n, var, strided, prm, outer);
 }
+
+// ---- real transforms (fft_pow2.cuh fft_real_body) stepped on the CPU: the same
+// phase functions, barriers where the kernel has __syncthreads()
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MODE>
+static int emu_real_one(const FftParams& prm_in, long long outer) {
+    using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
+    using C = cplx<T>;
+    FftParams prm = prm_in;
+    long long grid;
+    if (STRIDED) {
+        prm.tiles_per_outer = (prm.inner + P - 1) / P;
+        grid = outer * prm.tiles_per_outer;
+    } else {
+        grid = (prm.npencils + P - 1) / P;
+    }
+    std::vector<C> twv((size_t)RAD::tw_total()), rtw((size_t)N);
+    build_pass_twiddles<T, RAD>(twv.data());
+    build_real_twiddles<T>(rtw.data(), N);
+    const C* tw = twv.data();
+    std::vector<C> smem((size_t)TF::SI::tile_elems + P);
+    std::vector<C> regs((size_t)TF::THREADS * E);
+    const long long in_ns = STRIDED ? prm.in_nstride : 1, out_ns = STRIDED ? prm.out_nstride : 1;
+    for (long long bid = 0; bid < grid; ++bid) {
+        for (auto& x : smem) { x.x = (T)1e30; x.y = (T)-1e30; }
+        auto coords = [&](int tid, long long& o, long long& i, bool& valid) {
+            const int p = TF::pencil_of(tid);
+            if (STRIDED) {
+                o = bid / prm.tiles_per_outer;
+                i = (bid - o * prm.tiles_per_outer) * P + p;
+                valid = i < prm.inner;
+            } else {
+                o = bid * P + p;
+                i = 0;
+                valid = o < prm.npencils;
+            }
+        };
+        constexpr int R0 = RAD::get(0);
+        constexpr int RL = RAD::get(TF::NPASS - 1);
+        if (MODE == 1) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                C* v = &regs[(size_t)tid * E];
+                const int q = TF::slot_of(tid);
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                if (STRIDED) {
+                    const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+                    for (int b = 0; b < E / R0; ++b)
+                        for (int r = 0; r < R0; ++r) {
+                            const int n = q + b * TF::TP + r * (N / R0);
+                            C a = {(T)0, (T)0};
+                            if (valid) { a.x = gin[(long long)(2 * n) * in_ns]; a.y = gin[(long long)(2 * n + 1) * in_ns]; }
+                            v[b * R0 + r] = a;
+                        }
+                } else {
+                    TF::load_global(v, q, reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride, 1, valid, false);
+                }
+            }
+        } else {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                const int p = TF::pencil_of(tid), q = TF::slot_of(tid);
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                const C* gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+                for (int e = 0; e < E; ++e) {
+                    const int k = q + e * TF::TP;
+                    C a = {(T)0, (T)0};
+                    if (valid) a = gin[(long long)k * in_ns];
+                    smem[TF::SI::at(p, k)] = a;
+                }
+                if (q == 0) {
+                    C a = {(T)0, (T)0};
+                    if (valid) a = gin[(long long)N * in_ns];
+                    smem[TF::SI::tile_elems + p] = a;
+                }
+            }
+            // __syncthreads()
+            for (int tid = 0; tid < TF::THREADS; ++tid)
+                TF::c2r_pre(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data());
+            // __syncthreads()
+        }
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            C* v = &regs[(size_t)tid * E];
+            TF::template twiddle_dft<0>(v, TF::slot_of(tid), tw);
+            if (TF::NPASS > 1) TF::template store_shared<0>(v, TF::pencil_of(tid), TF::slot_of(tid), smem.data());
+        }
+        if constexpr (TF::NPASS > 1) {
+            EmuMid<TF, 1>::run(regs, smem.data(), tw);
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                C* v = &regs[(size_t)tid * E];
+                TF::template load_shared<TF::NPASS - 1>(v, TF::pencil_of(tid), TF::slot_of(tid), smem.data());
+                TF::template twiddle_dft<TF::NPASS - 1>(v, TF::slot_of(tid), tw);
+            }
+        }
+        if (MODE == 1) {
+            // __syncthreads()
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                const C* v = &regs[(size_t)tid * E];
+                const int p = TF::pencil_of(tid), q = TF::slot_of(tid);
+                for (int b = 0; b < E / RL; ++b)
+                    for (int r = 0; r < RL; ++r) smem[TF::SI::at(p, q + b * TF::TP + r * (N / RL))] = v[b * RL + r];
+            }
+            // __syncthreads()
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
+                TF::r2c_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale);
+            }
+        } else {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                const C* v = &regs[(size_t)tid * E];
+                const int q = TF::slot_of(tid);
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                if (STRIDED) {
+                    if (!valid) continue;
+                    T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                    for (int b = 0; b < E / RL; ++b)
+                        for (int r = 0; r < RL; ++r) {
+                            const int n = q + b * TF::TP + r * (N / RL);
+                            gout[(long long)(2 * n) * out_ns] = v[b * RL + r].y * (T)prm.scale;
+                            gout[(long long)(2 * n + 1) * out_ns] = v[b * RL + r].x * (T)prm.scale;
+                        }
+                } else {
+                    TF::store_global(v, q, reinterpret_cast<C*>(prm.out) + o * prm.out_ostride, 1, valid, true, (T)prm.scale);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+#define EMU_REAL_CONTIG(N, E, P, PS, MINB, ...)                                                          \
+    if (n == N) return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 1>(prm, outer) \
+                                 : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 2>(prm, outer);
+#define EMU_REAL_STRIDED(N, E, P, PS, MINB, ...)                                                         \
+    if (n == N)                                                                                          \
+        return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 1>(prm, outer) \
+                         : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 2>(prm, outer);
+
+template <class T>
+static int emu_real_dispatch(int n, int mode, bool strided, const FftParams& prm, long long outer) {
+    if (strided) {
+        B2F_REAL_STRIDED(EMU_REAL_STRIDED)
+    } else {
+        B2F_REAL_CONTIG(EMU_REAL_CONTIG)
+    }
+    return -1;
+}
+
+// (outer, nreal, inner) real <-> (outer, nreal/2+1, inner) complex; mode 1 = r2c, 2 = c2r
+extern "C" int emu_fft_real(int precision, int nreal, int mode, long long outer, long long inner, const void* in,
+                            void* out, double scale) {
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.in = in;
+    prm.out = out;
+    prm.scale = scale;
+    const int nc = nreal / 2;
+    const long long n_in = mode == 1 ? nreal : nc + 1, n_out = mode == 1 ? nc + 1 : nreal;
+    const bool strided = inner > 1;
+    if (strided) {
+        prm.in_ostride = n_in * inner;
+        prm.out_ostride = n_out * inner;
+        prm.in_nstride = prm.out_nstride = inner;
+        prm.inner = inner;
+    } else {
+        prm.in_ostride = mode == 1 ? nc : n_in;
+        prm.out_ostride = mode == 1 ? n_out : nc;
+        prm.npencils = outer;
+    }
+    if (precision == 8) return emu_real_dispatch<double>(nc, mode, strided, prm, outer);
+    return emu_real_dispatch<float>(nc, mode, strided, prm, outer);
+}

@@ -72,6 +72,9 @@ def main():
     modes = sorted(set('p2p' if v is not None else 'nccl' for v in fft._buffers.peers.values())) or ['nccl']
     if rank == 0:
         print('MULTI_OK cases=%d world=%d transfers=%s' % (ran, world, '+'.join(modes)), flush=True)
+    fft.destroy()
+    torch.cuda.synchronize()
+    comm.Barrier()
     import torch.distributed as dist
     dist.destroy_process_group()
 

@@ -100,6 +100,51 @@ def test_stockham_pow2_c2c(B, n, dt):
         _lib.set_option('variant', 0)
 
 
+@pytest.mark.parametrize('n', [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_stockham_real_transforms(B, n, dt):
+    """r2c / c2r of even power-of-two length through the n/2-point Stockham kernel
+    plus the split / merge pass (fft_real_kernel): contiguous and strided axis,
+    ragged tiles, fused normalisation, multi-axis stage, and the dense-matrix path
+    (real_engine=1) as a second witness on the same input"""
+    from mpi4py_fft_b200 import _lib
+    tol = TOL[dt]
+    shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 2048 else [(2, n), (n, 3)]
+    for shape in shapes:
+        axis = shape.index(n)
+        x = rand(shape, dt, seed=n + axis)
+        U = B.fftw.aligned(shape, dtype=dt)
+        U[...] = x
+        fwd = B.fftw.rfftn(U, axes=(axis,))
+        assert 'stockham-real' in fwd.plan().describe()
+        y = np.asarray(fwd(normalize=True)).copy()
+        ref = np.fft.rfft(x.astype('d'), axis=axis) / n
+        assert relerr(y, ref) < tol, ('r2c', n, dt, shape)
+        bck = B.fftw.irfftn(fwd.output_array, s=(n,), axes=(axis,), output_array=U)
+        z = bck()
+        assert relerr(z, x.astype('d')) < tol, ('c2r', n, dt, shape)
+        if n <= 512:
+            _lib.set_option('real_engine', 1)
+            try:
+                dense = B.fftw.rfftn(U, axes=(axis,))
+                U[...] = x
+                assert 'dense' in dense.plan().describe()
+                assert relerr(dense(normalize=True), y) < tol
+            finally:
+                _lib.set_option('real_engine', 0)
+    if n <= 1024:
+        # two-axis stage: r2c along the last listed axis, then c2c; and back
+        shape = (6, 16, n)
+        x = rand(shape, dt, seed=3)
+        U = B.fftw.aligned(shape, dtype=dt)
+        U[...] = x
+        fwd = B.fftw.rfftn(U, axes=(1, 2))
+        y = fwd(normalize=True)
+        assert relerr(y, np.fft.rfftn(x.astype('d'), axes=(1, 2)) / (16 * n)) < tol
+        bck = B.fftw.irfftn(fwd.output_array, s=(16, n), axes=(1, 2), output_array=U)
+        assert relerr(bck(), x.astype('d')) < tol
+
+
 @pytest.mark.parametrize('n', [64, 128, 256, 512, 1024, 2048])
 @pytest.mark.parametrize('dt', ['D', 'F'])
 def test_tma_staged_strided_c2c(B, n, dt):

@@ -70,3 +70,28 @@ def test_tma_staged_variants(emu, n, prec):
                 found += 1
                 assert err < tol, (n, prec, var, outer, inner, swap, err)
     assert found >= 4
+
+
+@pytest.mark.parametrize('nreal', [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize('prec', [8, 4])
+def test_real_transform_kernels(emu, nreal, prec):
+    """fft_real_body (r2c / c2r of even length 2N through the N-point schedule plus
+    the split / merge pass) against numpy.fft.rfft / irfft: contiguous and strided,
+    ragged tiles, fused scale; c2r ignores the imaginary parts of X[0] and X[N] as
+    FFTW does (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:57-67)"""
+    rt = np.float64 if prec == 8 else np.float32
+    ct = np.complex128 if prec == 8 else np.complex64
+    tol = 3e-15 if prec == 8 else 2e-6
+    rng = np.random.default_rng(nreal)
+    geos = ((3, 1), (2, 5), (1, 17)) if nreal <= 2048 else ((2, 1), (1, 3))
+    for outer, inner in geos:
+        x = rng.random((outer, nreal, inner)).astype(rt)
+        y = np.full((outer, nreal // 2 + 1, inner), np.nan, dtype=ct)
+        assert emu.emu_fft_real(prec, nreal, 1, outer, inner, x.ctypes.data, y.ctypes.data, 0.5) == 0
+        ref = np.fft.rfft(x.astype(np.float64), axis=1) * 0.5
+        assert np.abs(y - ref).max() / np.abs(ref).max() < tol, (nreal, prec, outer, inner, 'r2c')
+        X = (rng.random(y.shape) + 1j * rng.random(y.shape)).astype(ct)
+        z = np.full((outer, nreal, inner), np.nan, dtype=rt)
+        assert emu.emu_fft_real(prec, nreal, 2, outer, inner, X.copy().ctypes.data, z.ctypes.data, 1.0 / nreal) == 0
+        ref = np.fft.irfft(X.astype(np.complex128), n=nreal, axis=1)
+        assert np.abs(z - ref).max() / np.abs(ref).max() < tol, (nreal, prec, outer, inner, 'c2r')
