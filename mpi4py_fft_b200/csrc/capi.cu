@@ -24,6 +24,7 @@
 #include "dft_generic.h"
 #include "internal.h"
 #include "fft_configs.h"
+#include "chirpz_host.h"
 
 #define B2F_GENERIC_MAX_N 4096
 
@@ -121,8 +122,54 @@ const double* generic_matrix(int kind, long long n, int* rows, int* cols) {
     return d;
 }
 
+// chirp-z tables on the device, one set per (kind, n, precision, device)
+struct ChirpEntry {
+    void *pre, *filt, *post;
+    long long n_in, n_out;
+    int in_mode, out_real, M;
+};
+static std::map<DevKey, ChirpEntry> g_chirp;
+
+template <class T>
+static void* upload_ld(const std::vector<long double>& v) {
+    std::vector<T> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = (T)v[i];
+    void* d = nullptr;
+    if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+}
+
+static const ChirpEntry* chirp_tables(int kind, long long n, int precision) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevKey key{dev, kind * 16 + precision, n};
+    auto it = g_chirp.find(key);
+    if (it != g_chirp.end()) return &it->second;
+    ChirpSpec sp;
+    if (chirp_build(kind, n, &sp)) return nullptr;
+    ChirpEntry e;
+    e.n_in = sp.n_in;
+    e.n_out = sp.n_out;
+    e.in_mode = sp.in_mode;
+    e.out_real = sp.out_real;
+    e.M = sp.M;
+    if (precision == 8) {
+        e.pre = upload_ld<double>(sp.pre);
+        e.filt = upload_ld<double>(sp.filt);
+        e.post = upload_ld<double>(sp.post);
+    } else {
+        e.pre = upload_ld<float>(sp.pre);
+        e.filt = upload_ld<float>(sp.filt);
+        e.post = upload_ld<float>(sp.post);
+    }
+    if (!e.pre || !e.filt || !e.post) return nullptr;
+    return &(g_chirp[key] = e);
+}
+
 // ---- plan ------------------------------------------------------------------
-enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1, STEP_REAL = 2 };
+enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1, STEP_REAL = 2, STEP_CHIRP = 3 };
 enum Buf { BUF_IN = 0, BUF_OUT = 1 };
 
 struct Step {
@@ -138,6 +185,8 @@ struct Step {
     // generic
     const double* M;
     int rows, cols;
+    // chirp-z
+    const void* chirp;
 };
 
 // Default variant of the staged strided kernels (fft_configs.h B2F_TMA_TABLE /
@@ -165,6 +214,12 @@ static int staged_fallback(int n) {
 }
 
 static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+// does the chirp-z convolution of this transform fit the largest tile (M <= 8192)?
+static bool chirp_fits(int kind, long long n) {
+    const long long n_out = kind == B2F_R2C ? n / 2 + 1 : n;
+    return n >= 1 && n + n_out - 1 <= B2F_POW2_MAX_N && !(kind == B2F_REDFT00 && n < 2);
+}
 
 }  // namespace b2f
 
@@ -207,6 +262,22 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
             set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
             return B2F_EINVAL;
         }
+    } else if (option("generic_engine", 0) != 1 && (n > option("dense_max", 32) || option("generic_engine", 0) == 2) &&
+               chirp_fits(kind, n)) {
+        // any other length / kind: chirp-z convolution on two power-of-two FFTs
+        const ChirpEntry* ce = chirp_tables(kind, n, pl->precision);
+        if (!ce) {
+            set_error("cannot build chirp-z tables (kind " + std::to_string(kind) + ", n " + std::to_string(n) + ")");
+            return B2F_EINVAL;
+        }
+        const long long stored_in = ce->in_mode == 2 ? n / 2 + 1 : ce->n_in;
+        if (s.n_in != stored_in || s.n_out != ce->n_out || in_c != (ce->in_mode == 1 ? 1 : 2) ||
+            out_c != (ce->out_real ? 1 : 2)) {
+            set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
+            return B2F_EINVAL;
+        }
+        s.type = STEP_CHIRP;
+        s.chirp = ce;
     } else {
         if (n > B2F_GENERIC_MAX_N) {
             set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
@@ -448,6 +519,32 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             }
             e = pl->precision == 8 ? launch_real_f64((int)nc, mode, strided, prm, s.outer, st)
                                    : launch_real_f32((int)nc, mode, strided, prm, s.outer, st);
+        } else if (s.type == STEP_CHIRP) {
+            if (peer) {
+                set_error("fused redistribution needs a power-of-two c2c Stockham step last");
+                return B2F_EUNSUPPORTED;
+            }
+            const ChirpEntry* ce = reinterpret_cast<const ChirpEntry*>(s.chirp);
+            ChirpParams prm;
+            memset(&prm, 0, sizeof(prm));
+            prm.in = src;
+            prm.out = dst;
+            prm.pre = ce->pre;
+            prm.filt = ce->filt;
+            prm.post = ce->post;
+            prm.n_in = (int)ce->n_in;
+            prm.n_out = (int)ce->n_out;
+            prm.in_mode = ce->in_mode;
+            prm.out_real = ce->out_real;
+            prm.scale = sc;
+            const bool strided = s.inner > 1;
+            prm.in_ostride = s.n_in * s.inner;
+            prm.out_ostride = s.n_out * s.inner;
+            prm.in_nstride = prm.out_nstride = s.inner;
+            prm.inner = s.inner;
+            prm.npencils = s.outer;
+            e = pl->precision == 8 ? launch_chirp_f64(ce->M, strided, prm, s.outer, st)
+                                   : launch_chirp_f32(ce->M, strided, prm, s.outer, st);
         } else {
             if (peer) {
                 set_error("fused redistribution needs a power-of-two Stockham step last");
@@ -490,7 +587,8 @@ int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
         char line[256];
         snprintf(line, sizeof(line), "%s kind=%d axis=%d n_in=%lld n_out=%lld outer=%lld inner=%lld %s->%s\n",
                  st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig")
-                 : st.type == STEP_REAL ? (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig") : "dense-matrix",
+                 : st.type == STEP_REAL ? (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig")
+                 : st.type == STEP_CHIRP ? (st.inner > 1 ? "chirpz-strided" : "chirpz-contig") : "dense-matrix",
                  st.kind, st.axis, st.n_in, st.n_out, st.outer, st.inner,
                  st.src == BUF_IN ? "in" : "out", st.dst == BUF_IN ? "in" : "out");
         s += line;

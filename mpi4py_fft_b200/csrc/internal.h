@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include "fft_pow2.cuh"
+#include "chirpz.cuh"
 
 namespace b2f {
 
@@ -26,6 +27,10 @@ cudaError_t launch_pow2_large_f32(int n, int var, bool strided, const FftParams&
 // real transforms of even length 2n through the n-point schedule (fft_real_*.cu); mode 1 = r2c, 2 = c2r
 cudaError_t launch_real_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_real_f32(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+
+// chirp-z kernels (chirpz_*.cu): m = convolution length
+cudaError_t launch_chirp_f64(int m, bool strided, const ChirpParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_chirp_f32(int m, bool strided, const ChirpParams& prm, long long outer, cudaStream_t st);
 
 // TMA-staged strided c2c kernels (fft_tma_*.cu): one (outer, n, inner) step.
 // cudaErrorInvalidValue = (n, var) not built or the layout cannot be described

@@ -489,3 +489,137 @@ extern "C" int emu_fft_real(int precision, int nreal, int mode, long long outer,
     if (precision == 8) return emu_real_dispatch<double>(nc, mode, strided, prm, outer);
     return emu_real_dispatch<float>(nc, mode, strided, prm, outer);
 }
+
+// ---- chirp-z kernels (chirpz.cuh) stepped on the CPU -------------------------
+#include "../../mpi4py_fft_b200/csrc/chirpz.cuh"
+#include "../../mpi4py_fft_b200/csrc/chirpz_host.h"
+
+template <class TF>
+static void emu_chirp_fft(std::vector<typename TF::C>& regs, typename TF::C* smem, const typename TF::C* tw) {
+    using C = typename TF::C;
+    const int E = TF::EPT;
+    for (int tid = 0; tid < TF::THREADS; ++tid) {
+        C* v = &regs[(size_t)tid * E];
+        TF::template twiddle_dft<0>(v, TF::slot_of(tid), tw);
+        if (TF::NPASS > 1) TF::template store_shared<0>(v, TF::pencil_of(tid), TF::slot_of(tid), smem);
+    }
+    if constexpr (TF::NPASS > 1) {
+        EmuMid<TF, 1>::run(regs, smem, tw);
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            C* v = &regs[(size_t)tid * E];
+            TF::template load_shared<TF::NPASS - 1>(v, TF::pencil_of(tid), TF::slot_of(tid), smem);
+            TF::template twiddle_dft<TF::NPASS - 1>(v, TF::slot_of(tid), tw);
+        }
+    }
+}
+
+template <class T, int M, int E, class RAD, int P, bool STRIDED, int PS>
+static int emu_chirp_one(const ChirpParams& prm_in, long long outer) {
+    using TF = TileFFT<T, M, E, RAD, P, STRIDED, PS>;
+    using C = cplx<T>;
+    ChirpParams prm = prm_in;
+    long long grid;
+    if (STRIDED) {
+        prm.tiles_per_outer = (prm.inner + P - 1) / P;
+        grid = outer * prm.tiles_per_outer;
+    } else {
+        grid = (prm.npencils + P - 1) / P;
+    }
+    std::vector<C> twv((size_t)RAD::tw_total());
+    build_pass_twiddles<T, RAD>(twv.data());
+    std::vector<C> smem((size_t)TF::SI::tile_elems);
+    std::vector<C> regs((size_t)TF::THREADS * E);
+    const int in_size = prm.in_mode == 1 ? (int)sizeof(T) : (int)sizeof(C);
+    const int out_size = prm.out_real ? (int)sizeof(T) : (int)sizeof(C);
+    for (long long bid = 0; bid < grid; ++bid) {
+        for (auto& x : smem) { x.x = (T)1e30; x.y = (T)-1e30; }
+        auto coords = [&](int tid, long long& o, long long& i, bool& valid) {
+            const int p = TF::pencil_of(tid);
+            if (STRIDED) {
+                o = bid / prm.tiles_per_outer;
+                i = (bid - o * prm.tiles_per_outer) * P + p;
+                valid = i < prm.inner;
+            } else {
+                o = bid * P + p;
+                i = 0;
+                valid = o < prm.npencils;
+            }
+        };
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            long long o, i; bool valid;
+            coords(tid, o, i, valid);
+            const char* gin = reinterpret_cast<const char*>(prm.in) + (o * prm.in_ostride + i) * in_size;
+            chirp_phase_load<TF>(&regs[(size_t)tid * E], TF::slot_of(tid), gin, prm.in_nstride, valid, prm);
+        }
+        emu_chirp_fft<TF>(regs, smem.data(), twv.data());
+        // __syncthreads()
+        for (int tid = 0; tid < TF::THREADS; ++tid)
+            chirp_phase_filter<TF>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), smem.data(), prm);
+        // __syncthreads()
+        for (int tid = 0; tid < TF::THREADS; ++tid)
+            chirp_phase_reload<TF>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), smem.data());
+        // __syncthreads()
+        emu_chirp_fft<TF>(regs, smem.data(), twv.data());
+        for (int tid = 0; tid < TF::THREADS; ++tid) {
+            long long o, i; bool valid;
+            coords(tid, o, i, valid);
+            char* gout = reinterpret_cast<char*>(prm.out) + (o * prm.out_ostride + i) * out_size;
+            chirp_phase_store<TF>(&regs[(size_t)tid * E], TF::slot_of(tid), gout, prm.out_nstride, valid, prm);
+        }
+    }
+    return 0;
+}
+
+#define EMU_CHIRP_CONTIG(N, E, P, PS, MINB, ...) \
+    if (m == N) return emu_chirp_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS>(prm, outer);
+#define EMU_CHIRP_STRIDED(N, E, P, PS, MINB, ...) \
+    if (m == N) return emu_chirp_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS>(prm, outer);
+
+template <class T>
+static int emu_chirp_dispatch(int m, bool strided, const ChirpParams& prm, long long outer) {
+    if (strided) {
+        B2F_REAL_STRIDED(EMU_CHIRP_STRIDED)
+    } else {
+        B2F_REAL_CONTIG(EMU_CHIRP_CONTIG)
+    }
+    return -1;
+}
+
+// (outer, n_stored_in, inner) -> (outer, n_stored_out, inner) along the middle axis;
+// kind = FFTW integer, n = logical length
+extern "C" int emu_chirpz(int precision, int kind, long long n, long long outer, long long inner, const void* in,
+                          void* out, double scale) {
+    ChirpSpec sp;
+    if (chirp_build(kind, n, &sp)) return -2;
+    ChirpParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    std::vector<double> pre8, filt8, post8;
+    std::vector<float> pre4, filt4, post4;
+    auto conv = [](const std::vector<long double>& v, std::vector<double>& d, std::vector<float>& f) {
+        d.resize(v.size());
+        f.resize(v.size());
+        for (size_t i = 0; i < v.size(); ++i) { d[i] = (double)v[i]; f[i] = (float)v[i]; }
+    };
+    conv(sp.pre, pre8, pre4);
+    conv(sp.filt, filt8, filt4);
+    conv(sp.post, post8, post4);
+    prm.in = in;
+    prm.out = out;
+    prm.pre = precision == 8 ? (const void*)pre8.data() : (const void*)pre4.data();
+    prm.filt = precision == 8 ? (const void*)filt8.data() : (const void*)filt4.data();
+    prm.post = precision == 8 ? (const void*)post8.data() : (const void*)post4.data();
+    prm.n_in = (int)sp.n_in;
+    prm.n_out = (int)sp.n_out;
+    prm.in_mode = sp.in_mode;
+    prm.out_real = sp.out_real;
+    prm.scale = scale;
+    const long long stored_in = sp.in_mode == 2 ? n / 2 + 1 : sp.n_in;
+    prm.in_ostride = stored_in * inner;
+    prm.out_ostride = sp.n_out * inner;
+    prm.in_nstride = prm.out_nstride = inner;
+    prm.inner = inner;
+    prm.npencils = outer;
+    const bool strided = inner > 1;
+    if (precision == 8) return emu_chirp_dispatch<double>(sp.M, strided, prm, outer);
+    return emu_chirp_dispatch<float>(sp.M, strided, prm, outer);
+}

@@ -125,13 +125,20 @@ def test_stockham_real_transforms(B, n, dt):
         assert relerr(z, x.astype('d')) < tol, ('c2r', n, dt, shape)
         if n <= 512:
             _lib.set_option('real_engine', 1)
+            _lib.set_option('generic_engine', 1)
             try:
                 dense = B.fftw.rfftn(U, axes=(axis,))
                 U[...] = x
                 assert 'dense' in dense.plan().describe()
                 assert relerr(dense(normalize=True), y) < tol
+                _lib.set_option('generic_engine', 2)
+                chirp = B.fftw.rfftn(U, axes=(axis,))
+                U[...] = x
+                assert 'chirpz' in chirp.plan().describe()
+                assert relerr(chirp(normalize=True), y) < tol
             finally:
                 _lib.set_option('real_engine', 0)
+                _lib.set_option('generic_engine', 0)
     if n <= 1024:
         # two-axis stage: r2c along the last listed axis, then c2c; and back
         shape = (6, 16, n)
@@ -289,11 +296,69 @@ def test_generic_lengths_c2c(B, n, dft_ref):
         p = B.fftw.fftn(U, axes=(axis,))
         y = np.asarray(p())
         assert relerr(y, np.fft.fft(z, axis=axis)) < 1e-12
-        assert 'dense-matrix' in p.plan().describe()
+        assert ('dense-matrix' if n <= 32 else 'chirpz') in p.plan().describe()
     z = rand((n,), 'D', 1)
     U = B.fftw.aligned((n,), dtype='D')
     U[...] = z
     assert relerr(B.fftw.fftn(U)(), dft_ref(-1, n, z)) < 1e-12
+
+
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_chirpz_every_kind_any_length(B, dt, dft_ref):
+    """chirp-z kernels forced for every length (generic_engine=2): c2c both signs,
+    r2c, c2r (odd and even lengths), the eight r2r kinds, contiguous and strided,
+    against numpy / scipy, the O(n^2) restatement of the FFTW definitions and the
+    dense-matrix path; plus the sizes a 3/2-rule padded solver uses"""
+    import scipy.fft as sfft
+    from mpi4py_fft_b200 import _lib
+    fftw = B.fftw
+    tol = TOL[dt] * (5 if dt == 'f' else 1)
+    cd = dt.upper()
+    _lib.set_option('generic_engine', 2)
+    try:
+        for n in (5, 6, 7, 12, 13, 30, 100, 127, 384, 1000, 1536):
+            for shape, axis in (((3, n), 1), ((n, 5), 0)):
+                z = rand(shape, cd, n)
+                U = fftw.aligned(shape, dtype=cd)
+                U[...] = z
+                pf = fftw.fftn(U, axes=(axis,))
+                assert 'chirpz' in pf.plan().describe()
+                y = np.asarray(pf()).copy()
+                assert relerr(y, np.fft.fft(z.astype('D'), axis=axis)) < tol, ('c2c', n, shape)
+                pb = fftw.ifftn(pf.output_array, axes=(axis,), output_array=U)
+                assert relerr(pb(normalize=True), z.astype('D')) < tol, ('c2c inverse', n, shape)
+                x = rand(shape, dt, n + 1)
+                R = fftw.aligned(shape, dtype=dt)
+                R[...] = x
+                pr = fftw.rfftn(R, axes=(axis,))
+                assert 'chirpz' in pr.plan().describe()
+                assert relerr(pr(), np.fft.rfft(x.astype('d'), axis=axis)) < tol, ('r2c', n, shape)
+                pc = fftw.irfftn(pr.output_array, s=(n,), axes=(axis,), output_array=R)
+                assert relerr(pc(normalize=True), x.astype('d')) < tol, ('c2r', n, shape)
+                if n <= 384:
+                    for typ in (1, 2, 3, 4):
+                        for fam, planner in (('dct', fftw.dctn), ('dst', fftw.dstn)):
+                            R[...] = x
+                            pp = planner(R, axes=(axis,), type=typ)
+                            assert 'chirpz' in pp.plan().describe()
+                            ref = getattr(sfft, fam)(x.astype('d'), type=typ, axis=axis)
+                            assert relerr(pp(), ref) < tol, (fam, typ, n, shape)
+        # definitions (long double, O(n^2)) and the dense path as second witnesses
+        n = 45
+        x = rand((n,), dt, 7)
+        R = fftw.aligned((n,), dtype=dt)
+        for kind in range(3, 11):
+            R[...] = x
+            out = fftw.aligned((n,), dtype=dt)
+            got = np.asarray(fftw.FFT(R, out, axes=(0,), kind=kind)()).copy()
+            assert relerr(got, dft_ref(kind, n, x.astype('d'))) < tol, kind
+            _lib.set_option('generic_engine', 1)
+            dense = fftw.FFT(R, out, axes=(0,), kind=kind)
+            assert 'dense' in dense.plan().describe()
+            assert relerr(dense(), got) < tol, kind
+            _lib.set_option('generic_engine', 2)
+    finally:
+        _lib.set_option('generic_engine', 0)
 
 
 @pytest.mark.parametrize('backendless', [True])

@@ -95,3 +95,49 @@ def test_real_transform_kernels(emu, nreal, prec):
         assert emu.emu_fft_real(prec, nreal, 2, outer, inner, X.copy().ctypes.data, z.ctypes.data, 1.0 / nreal) == 0
         ref = np.fft.irfft(X.astype(np.complex128), n=nreal, axis=1)
         assert np.abs(z - ref).max() / np.abs(ref).max() < tol, (nreal, prec, outer, inner, 'c2r')
+
+
+def _chirp_case(emu, dft_ref, prec, kind, n, outer, inner, seed=0):
+    rt = np.float64 if prec == 8 else np.float32
+    ct = np.complex128 if prec == 8 else np.complex64
+    rng = np.random.default_rng(seed)
+    n_in = n // 2 + 1 if kind == 2 else n
+    n_out = n // 2 + 1 if kind == -2 else n
+    in_complex = kind in (-1, 1, 2)
+    out_complex = kind in (-1, 1, -2)
+    x = rng.random((outer, n_in, inner))
+    if in_complex:
+        x = x + 1j * rng.random((outer, n_in, inner))
+    x = x.astype(ct if in_complex else rt)
+    y = np.full((outer, n_out, inner), np.nan, dtype=ct if out_complex else rt)
+    rc = emu.emu_chirpz(prec, kind, n, outer, inner, x.ctypes.data, y.ctypes.data, 0.25)
+    assert rc == 0, (kind, n, rc)
+    ref = np.empty(y.shape, dtype=complex if out_complex else float)
+    for o in range(outer):
+        for i in range(inner):
+            ref[o, :, i] = dft_ref(kind, n, x[o, :, i].astype(complex if in_complex else float)) * 0.25
+    return np.abs(y - ref).max() / np.abs(ref).max()
+
+
+@pytest.mark.parametrize('kind', [-1, 1, -2, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize('prec', [8, 4])
+def test_chirpz_all_kinds_any_length(emu, dft_ref, kind, prec):
+    """chirpz.cuh (pre-chirp, M-point FFT, filter, M-point FFT, post-chirp) for every
+    transform kind the reference can ask FFTW for (fftw_planxfftn.c:49-76), odd /
+    prime / composite lengths, against the O(n^2) long double restatement of the
+    FFTW definitions (oracle/dft_ref.c); contiguous and strided with ragged tiles"""
+    tol = 2e-14 if prec == 8 else 2e-5
+    for n in (2, 3, 5, 6, 7, 12, 13, 31, 33, 64, 100, 127, 191):
+        if kind == 3 and n < 2:
+            continue
+        for outer, inner in ((2, 1), (1, 5)):
+            err = _chirp_case(emu, dft_ref, prec, kind, n, outer, inner, seed=n)
+            assert err < tol, (kind, prec, n, outer, inner, err)
+
+
+@pytest.mark.parametrize('n', [384, 1000, 1536, 2187, 4096])
+def test_chirpz_large_lengths(emu, dft_ref, n):
+    """3/2-rule sizes and the largest length that fits one tile (M = 8192)"""
+    for kind in (-1, 5):
+        err = _chirp_case(emu, dft_ref, 8, kind, n, 1, 1 if n > 1000 else 3, seed=1)
+        assert err < 5e-14, (kind, n, err)
