@@ -105,6 +105,19 @@ B2F_API int b2f_destroy_plan(b2f_plan plan);
 /* one line per stage: kernel family, N, batch geometry (print_plan analogue) */
 B2F_API int b2f_plan_describe(b2f_plan plan, char *buf, size_t buflen);
 
+/*
+ * Dealiasing step of a padded transform along one axis of an (outer, n, inner)
+ * complex block: mode 0 truncates a padded spectrum (n_src = padded, n_dst = kept
+ * modes), mode 1 zero-pads it back; half_spectrum != 0 for the r2c layout.
+ * Same mode selection and Nyquist treatment as FFTBase._truncation_forward /
+ * _padding_backward (/root/reference/mpi4py_fft/libfft.py:263-311); `scale` is
+ * applied on the way (the reference's `*= M`, libfft.py:412-413).
+ */
+B2F_API int b2f_pad_truncate(int mode, int half_spectrum, int precision,
+                     const void *d_src, void *d_dst,
+                     int64_t outer, int64_t n_src, int64_t n_dst, int64_t inner,
+                     double scale, void *stream);
+
 /* ---- (2) global transpose --------------------------------------------- */
 /* NCCL communicator for one 1-D process group (replaces the MPI
  * sub-communicator of MPI_Cart_sub, pencil.py:84-88).  The 128-byte id is

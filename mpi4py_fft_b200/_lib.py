@@ -29,6 +29,8 @@ SYMBOLS = {
     'b2f_execute': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     'b2f_destroy_plan': (C.c_int, [C.c_void_p]),
     'b2f_plan_describe': (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    'b2f_pad_truncate': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_double, C.c_void_p]),
     'b2f_comm_unique_id': (C.c_int, [C.c_void_p]),
     'b2f_comm_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]),
     'b2f_comm_destroy': (C.c_int, [C.c_void_p]),
@@ -163,6 +165,13 @@ class Plan(object):
             self.destroy()
         except Exception:
             pass
+
+
+def pad_truncate(mode, half_spectrum, precision, src_ptr, dst_ptr, outer, n_src, n_dst, inner, scale=1.0):
+    """b2f_pad_truncate on the current stream (mode 0 truncate, 1 pad)"""
+    check(lib().b2f_pad_truncate(int(mode), 1 if half_spectrum else 0, int(precision), C.c_void_p(src_ptr),
+                                 C.c_void_p(dst_ptr), int(outer), int(n_src), int(n_dst), int(inner), float(scale),
+                                 current_stream_ptr()), 'b2f_pad_truncate')
 
 
 # ---------------------------------------------------------------------------

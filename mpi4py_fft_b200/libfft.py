@@ -122,6 +122,109 @@ class _Stage(object):
         return dst
 
 
+class _PaddedStage(_Stage):
+    """One direction of a padded (dealiased) serial stage: the transform runs at
+    the padded length, the spectrum is truncated (forward) or zero padded
+    (backward) by ``b2f_pad_truncate`` with the reference's Nyquist rule
+    (libfft.py:263-311, 408-422).  Normalisation is by the padded length and is
+    fused into the truncation pass (forward) or the last FFT pass (backward)."""
+
+    def __init__(self, owner, planned, default_normalize, forward):
+        _Stage.__init__(self, owner, planned, default_normalize)
+        self._forward = forward
+
+    @property
+    def input_shape(self):
+        return self._planned.input_shape if self._forward else self._owner.trunc_shape
+
+    @property
+    def output_shape(self):
+        return self._owner.trunc_shape if self._forward else self._planned.output_shape
+
+    @property
+    def input_dtype(self):
+        return self._planned.input_dtype if self._forward else self._owner.trunc_dtype
+
+    @property
+    def output_dtype(self):
+        return self._owner.trunc_dtype if self._forward else self._planned.output_dtype
+
+    @property
+    def destroys_input(self):
+        return False
+
+    def run(self, src, dst, normalize=None):
+        from ._lib import pad_truncate
+        from .devarray import device_ptr
+        if normalize is None:
+            normalize = self._default_normalize
+        own = self._owner
+        axis = own.axes[-1]
+        spec_shape = own.fwd.output_shape                   # padded spectrum
+        outer = int(np.prod(spec_shape[:axis])) if axis else 1
+        inner = int(np.prod(spec_shape[axis + 1:])) if axis + 1 < len(spec_shape) else 1
+        n_pad, n_keep = spec_shape[axis], own.trunc_shape[axis]
+        scale = own.M if normalize else 1.0
+        Vp = own._array(own.fwd, 'out')                    # the padded spectrum, plan owned
+        if self._forward:
+            assert tuple(dst.shape) == own.trunc_shape
+            self._planned.execute(src, Vp, 1.0)
+            pad_truncate(0, own.real_transform, own.fwd.precision, device_ptr(Vp), device_ptr(dst),
+                         outer, n_pad, n_keep, inner, scale)
+        else:
+            assert tuple(src.shape) == own.trunc_shape
+            pad_truncate(1, own.real_transform, own.fwd.precision, device_ptr(src), device_ptr(Vp),
+                         outer, n_keep, n_pad, inner, 1.0)
+            self._planned.execute(Vp, dst, scale)
+        return dst
+
+    def can_scatter(self, transfer_handle, direction):
+        # forward: the truncation pass comes last, nothing to fuse; backward: the
+        # transform at the padded length is last and can store into the windows
+        return (not self._forward) and _Stage.can_scatter(self, transfer_handle, direction)
+
+    def run_scatter(self, src, work, normalize, transfer_handle, direction, peer_ptrs):
+        from ._lib import pad_truncate
+        from .devarray import device_ptr
+        assert not self._forward
+        if normalize is None:
+            normalize = self._default_normalize
+        own = self._owner
+        axis = own.axes[-1]
+        spec_shape = own.fwd.output_shape
+        outer = int(np.prod(spec_shape[:axis])) if axis else 1
+        inner = int(np.prod(spec_shape[axis + 1:])) if axis + 1 < len(spec_shape) else 1
+        Vp = own._array(own.fwd, 'out')
+        pad_truncate(1, own.real_transform, own.fwd.precision, device_ptr(src), device_ptr(Vp),
+                     outer, own.trunc_shape[axis], spec_shape[axis], inner, 1.0)
+        self._planned.execute_scatter(Vp, work, own.M if normalize else 1.0, transfer_handle, direction, peer_ptrs)
+
+    def __call__(self, input_array=None, output_array=None, **kw):
+        normalize = kw.pop('normalize', self._default_normalize)
+        src = self._planned._usable(input_array, self.input_shape, self.input_dtype)
+        if src is None:
+            src = self.input_array
+            if input_array is not None:
+                src[...] = input_array
+        dst = self._planned._usable(output_array, self.output_shape, self.output_dtype)
+        direct = dst is not None
+        if dst is None:
+            dst = self.output_array
+        self.run(src, dst, normalize)
+        if output_array is not None and not direct:
+            _copy_out(dst, output_array)
+            return output_array
+        return dst
+
+    @property
+    def input_array(self):
+        return self._owner._array(self._owner.fwd, 'in') if self._forward else self._owner._trunc()
+
+    @property
+    def output_array(self):
+        return self._owner._trunc() if self._forward else self._owner._array(self._owner.fwd, 'in')
+
+
 class FFTBase(object):
     """Argument normalisation shared by serial transforms (reference
     libfft.py:221-261)."""
@@ -166,17 +269,35 @@ class FFT(FFTBase):
         pf = 1.0
         if padding is not False:
             pf = padding[self.axes[-1]] if np.ndim(padding) else padding
-        if abs(pf - 1.0) > 1e-8:
-            raise NotImplementedError("padded (dealiased) transforms are not part of this build yet")
-        self.padding_factor = 1.0
+        self.padding_factor = float(pf)
         self.backend = backend
         self.fwd, self.bck = _Xfftn_plan_b200(self.shape, self.axes, self.dtype, transforms, kw)
         self.M = self.fwd.get_normalization()
         # the two plan-owned arrays: physical side U, spectral side V
         self._U = None
         self._V = None
-        self.forward = _Stage(self, self.fwd, True)
-        self.backward = _Stage(self, self.bck, False)
+        self._T = None
+        if abs(pf - 1.0) > 1e-8:
+            # padded stage: `shape` is the padded physical shape, the spectrum keeps
+            # round(n / factor) modes (libfft.py:401-406, 424-434)
+            assert len(self.axes) == 1
+            assert self.fwd.kind in (fftw.FFTW_FORWARD, fftw.R2C), "padding needs a Fourier stage"
+            axis = self.axes[-1]
+            tshape = list(self.fwd.output_shape)
+            keep = int(np.round(self.shape[axis] / pf))
+            tshape[axis] = keep // 2 + 1 if self.real_transform else keep
+            self.trunc_shape = tuple(tshape)
+            self.trunc_dtype = self.fwd.output_dtype
+            self.forward = _PaddedStage(self, self.fwd, True, True)
+            self.backward = _PaddedStage(self, self.bck, False, False)
+        else:
+            self.forward = _Stage(self, self.fwd, True)
+            self.backward = _Stage(self, self.bck, False)
+
+    def _trunc(self):
+        if self._T is None:
+            self._T = ArraySpec(self.trunc_shape, self.trunc_dtype).allocate()
+        return self._T
 
     def _array(self, planned, side):
         physical = (planned is self.fwd) == (side == 'in')

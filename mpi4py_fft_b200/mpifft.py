@@ -351,7 +351,7 @@ class PFFT(object):
     Parameters are the reference's (mpifft.py:82-204): ``comm`` (a communicator
     of this package, a :class:`Subcomm`, or a Cartesian communicator), ``shape``,
     ``axes`` (None | int | sequence of ints | sequence of sequences),
-    ``dtype``, ``grid``, ``padding`` (must be False in this build), ``collapse``,
+    ``dtype``, ``grid``, ``padding`` (False or one factor per axis), ``collapse``,
     ``backend`` (ignored: device kernels), ``transforms`` (axes tuple ->
     (forward planner, backward planner) from :mod:`mpi4py_fft_b200.fftw`),
     ``darray``, ``slab`` (deprecated).
@@ -399,7 +399,15 @@ class PFFT(object):
             dtype = np.dtype(dtype)
             assert dtype.char in 'fdgFDG'
             if padding is not False:
-                raise NotImplementedError("padded (dealiased) PFFT is not part of this build yet")
+                # the physical shape grows along every padded single-axis stage and the
+                # factor becomes the exact ratio (reference mpifft.py:247-253)
+                padding = list(padding)
+                assert len(padding) == len(shape)
+                for grp in groups:
+                    if len(grp) == 1 and padding[grp[0]] > 1.0 + 1e-6:
+                        old = float(shape[grp[0]])
+                        shape[grp[0]] = int(np.floor(shape[grp[0]] * padding[grp[0]]))
+                        padding[grp[0]] = shape[grp[0]] / old
             self._input_shape = tuple(shape)
             assert len(shape) > 0
             assert min(shape) > 0

@@ -46,6 +46,22 @@ CASES = {
     'c2c_4d_nested_p4': (4, dict(shape=(6, 8, 5, 7), dtype='D', axes=((0,), (1,), (2, 3))), True),
     'r2c_3d_nested_collapse_p4': (4, dict(shape=(12, 13, 8), dtype='d', axes=((0,), (1, 2)), collapse=True), True),
     'c2c_32_p1': (1, dict(shape=(32, 32, 32), dtype='D'), False),
+    # padded (dealiased) transforms, mpifft.py:247-253 + libfft.py:263-311; shape = the truncated size
+    'pad_c2c_8_p4_3half': (4, dict(shape=(8, 8, 8), dtype='D', padding=[1.5, 1.5, 1.5]), True),
+    'pad_r2c_8_12_10_p4_3half': (4, dict(shape=(8, 12, 10), dtype='d', padding=[1.5, 1.5, 1.5]), True),
+    'pad_c2c_9_7_p2_mixed': (2, dict(shape=(9, 7), dtype='D', padding=[2, 1.5]), True),
+    'pad_r2c_10_9_8_p1': (1, dict(shape=(10, 9, 8), dtype='d', padding=[1.5, 1.0, 1.5]), True),
+}
+
+# serial padded stages (libfft.FFT with padding): shape (already padded), axis, dtype, factor
+SERIAL_PAD = {
+    'spad_c_even': ((5, 12, 3), 1, 'D', 1.5),
+    'spad_c_odd': ((4, 15), 1, 'D', 1.5),
+    'spad_c_first_axis': ((18, 4), 0, 'D', 2.0),
+    'spad_r_even_half': ((3, 12), 1, 'd', 1.5),     # kept 8 -> half spectrum 5 (odd)
+    'spad_r_odd_half': ((3, 18), 1, 'd', 1.5),      # kept 12 -> half spectrum 7
+    'spad_r_evenhalf2': ((2, 9, 4), 1, 'd', 1.5),   # kept 6 -> half spectrum 4 (even: Nyquist rule fires)
+    'spad_r_first_axis': ((15, 4), 0, 'd', 1.5),    # kept 10 -> half spectrum 6 (even)
 }
 
 
@@ -57,6 +73,9 @@ CASES = {
 
 def rank_body(kw, want_values, seed):
     comm = MPI.COMM_WORLD
+    kw = dict(kw)
+    if 'padding' in kw:
+        kw['padding'] = list(kw['padding'])     # the reference rewrites the list in place (mpifft.py:253)
     fft = PFFT(comm, backend='numpy', **kw)
     info = dict(
         subcomm_sizes=[c.Get_size() for c in fft.subcomm],
@@ -112,6 +131,26 @@ def main():
             values[name + '__forward'] = fwd
             values[name + '__backward'] = bwd
         print('%-36s ranks=%d grid=%s out=%s' % (name, nranks, res[0][0]['subcomm_sizes'], res[0][0]['output_shape']))
+
+    # serial padded stages through the reference's own libfft.FFT (numpy backend)
+    from mpi4py_fft.libfft import FFT as RefFFT
+    for seed, (name, (shape, axis, dt, pf)) in enumerate(sorted(SERIAL_PAD.items())):
+        f = RefFFT(shape, axes=(axis,), dtype=dt, padding=pf, backend='numpy')
+        rng = np.random.default_rng(100 + seed)
+        x = rng.random(shape)
+        if dt in 'FD':
+            x = x + 1j * rng.random(shape)
+        x = x.astype(dt)
+        f.forward.input_array[...] = x
+        y = np.array(f.forward()).copy()
+        f.backward.input_array[...] = y
+        z = np.array(f.backward()).copy()
+        values[name + '__input'] = x
+        values[name + '__forward'] = y
+        values[name + '__backward'] = z
+        layouts['_' + name] = dict(shape=list(shape), axis=axis, dtype=dt, padding=pf,
+                                   trunc_shape=list(y.shape), trunc_dtype=y.dtype.char)
+        print('%-36s %s -> %s' % (name, shape, y.shape))
 
     # stand-alone layout goldens quoted in the reference's docstrings
     def pencil_doc():

@@ -15,6 +15,9 @@ What is restated (numpy, all ranks of the job simulated in one process):
   plan              mpifft.py:213-337 (axes groups, grid, collapse, r2c shape
                     and dtype propagation)
   stage             libfft.py:408-422 (forward *= M, backward unnormalised)
+  padding           mpifft.py:247-253 (padded physical shape), libfft.py:263-311
+                    (spectral truncation / zero padding with the symmetric
+                    Nyquist rule), libfft.py:424-434 (truncated extents)
   serial transforms the FFTW definitions (third party, un-vendored, no version
                     pinned by the reference: setup.py:64-81 probes library
                     names only) evaluated with numpy/scipy pocketfft: c2c
@@ -130,6 +133,76 @@ def serial_c2r(a, axes, s):
     return sfft.irfftn(a, s=s, axes=axes, norm='forward')
 
 
+def truncate_forward(padded, axis, n_trunc, real):
+    """libfft.py:263-286: keep n_trunc modes of a padded spectrum along ``axis``
+    (n_trunc = extent of the truncated array: N for complex, N//2+1 for r2c)"""
+    shape = list(padded.shape)
+    shape[axis] = n_trunc
+    trunc = np.zeros(shape, dtype=padded.dtype)
+    N = n_trunc
+    if real:
+        s = [slice(None)] * trunc.ndim
+        s[axis] = slice(0, N)
+        trunc[:] = padded[tuple(s)]
+        if N % 2 == 0:          # the reference tests the truncated array's own extent (libfft.py:267,274)
+            s[axis] = N - 1
+            s = tuple(s)
+            trunc[s] = trunc[s].real
+            trunc[s] *= 2
+    else:
+        su = [slice(None)] * trunc.ndim
+        su[axis] = slice(0, N // 2 + 1)
+        trunc[tuple(su)] = padded[tuple(su)]
+        su[axis] = slice(-(N // 2), None)
+        trunc[tuple(su)] += padded[tuple(su)]
+    return trunc
+
+
+def pad_backward(trunc, axis, n_padded, real):
+    """libfft.py:288-311: zero-pad a truncated spectrum to n_padded along ``axis``"""
+    shape = list(trunc.shape)
+    shape[axis] = n_padded
+    padded = np.zeros(shape, dtype=trunc.dtype)
+    N = trunc.shape[axis]
+    if real:
+        s = [slice(0, n) for n in trunc.shape]
+        padded[tuple(s)] = trunc[:]
+        if N % 2 == 0:
+            s[axis] = N - 1
+            s = tuple(s)
+            padded[s] = padded[s].real
+            padded[s] *= 0.5
+    else:
+        su = [slice(None)] * trunc.ndim
+        su[axis] = slice(0, N // 2 + 1)
+        padded[tuple(su)] = trunc[tuple(su)]
+        su[axis] = slice(-(N // 2), None)
+        padded[tuple(su)] = trunc[tuple(su)]
+        if N % 2 == 0:
+            su[axis] = N // 2
+            padded[tuple(su)] *= 0.5
+            su[axis] = -(N // 2)
+            padded[tuple(su)] *= 0.5
+    return padded
+
+
+def padded_stage_forward(x, axis, pf, normalize=True):
+    """one serial padded stage, libfft.py:376-415 with 424-434: x has the padded
+    extent along ``axis``"""
+    real = not np.iscomplexobj(x)
+    Np = x.shape[axis]
+    V = sfft.rfft(x, axis=axis) if real else sfft.fft(x, axis=axis)
+    N = int(np.round(Np / pf))
+    out = truncate_forward(V, axis, N // 2 + 1 if real else N, real)
+    return out / Np if normalize else out
+
+
+def padded_stage_backward(y, axis, n_padded, real, normalize=False):
+    V = pad_backward(y, axis, n_padded // 2 + 1 if real else n_padded, real)
+    x = sfft.irfft(V, n=n_padded, axis=axis, norm='forward') if real else sfft.ifft(V, axis=axis, norm='forward')
+    return x / n_padded if normalize else x
+
+
 class OraclePFFT(object):
     """All ranks of a PFFT at once.
 
@@ -139,7 +212,7 @@ class OraclePFFT(object):
     """
 
     def __init__(self, nranks, shape, axes=None, dtype=float, grid=None, collapse=False,
-                 transforms=None, subcomm_dims_arg=None):
+                 transforms=None, subcomm_dims_arg=None, padding=False):
         self.nranks = nranks
         ndim = len(shape)
         # ---- axes normalisation (mpifft.py:213-240)
@@ -154,6 +227,16 @@ class OraclePFFT(object):
                 axes[i] = tuple(a + ndim if a < 0 else a for a in ax)
         shape = list(shape)
         dtype = np.dtype(dtype)
+        # ---- padding: the physical shape grows, the factor becomes the exact ratio (mpifft.py:247-253)
+        if padding is not False:
+            padding = list(padding)
+            assert len(padding) == len(shape)
+            for ax in axes:
+                if len(ax) == 1 and padding[ax[0]] > 1.0 + 1e-6:
+                    old = float(shape[ax[0]])
+                    shape[ax[0]] = int(np.floor(shape[ax[0]] * padding[ax[0]]))
+                    padding[ax[0]] = shape[ax[0]] / old
+        self.padding = padding
         self.input_shape = tuple(shape)
         # ---- process grid (mpifft.py:259-290)
         if grid is not None:
@@ -190,6 +273,16 @@ class OraclePFFT(object):
             real = np.issubdtype(dt, np.floating)
             oshape = list(gshape)
             odt = dt
+            pf = 1.0 if self.padding is False else self.padding[grp[-1]]
+            if abs(pf - 1.0) > 1e-8:
+                # padded stage (libfft.py:401-406,424-434): one axis, spectrum truncated
+                assert len(grp) == 1 and grp not in transforms
+                N = int(np.round(gshape[grp[0]] / pf))
+                oshape[grp[0]] = N // 2 + 1 if real else N
+                odt = np.dtype(dt.char.upper())
+                return dict(axes=grp, kinds_f=[R2C if real else FORWARD], kinds_b=[C2R if real else BACKWARD],
+                            M=1.0 / gshape[grp[0]], in_gshape=tuple(gshape), out_gshape=tuple(oshape),
+                            in_dtype=dt, out_dtype=odt, pencils_in=pencils, pad=pf)
             if grp in transforms:
                 fam, typ = transforms[grp]
                 kf, kb = (DCT if fam == 'dct' else DST)[typ]
@@ -319,6 +412,10 @@ class OraclePFFT(object):
         for i, st in enumerate(self.stages):
             nxt = []
             for b in cur:
+                if 'pad' in st:
+                    v = padded_stage_forward(b.astype(st['in_dtype'], copy=False), st['axes'][0], st['pad'], normalize)
+                    nxt.append(v.astype(st['out_dtype'], copy=False))
+                    continue
                 v = serial_transform(b.astype(st['in_dtype'], copy=False), st['axes'], st['kinds_f'])
                 if normalize:
                     v = v * st['M']
@@ -335,6 +432,12 @@ class OraclePFFT(object):
             st = self.stages[i]
             nxt = []
             for r, b in enumerate(cur):
+                if 'pad' in st:
+                    ax = st['axes'][0]
+                    v = padded_stage_backward(b, ax, st['pencils_in'][r].subshape[ax],
+                                              np.issubdtype(st['in_dtype'], np.floating), normalize)
+                    nxt.append(v.astype(st['in_dtype'], copy=False))
+                    continue
                 if st['kinds_b'][0] == C2R:
                     s = [st['pencils_in'][r].subshape[a] for a in st['axes']]
                     v = serial_c2r(b, st['axes'], s)

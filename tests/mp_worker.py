@@ -41,7 +41,8 @@ def main():
         assert err <= tol * max(1.0, np.abs(ref).max()), (name, rank, err)
         ub = B.newDistArray(fft, False)
         fft.backward(uh, ub)
-        err = np.abs(np.asarray(ub) - g[fft.local_slice(False)]).max()
+        refb = values[name + '__backward']        # == g except for padded (lossy) transforms
+        err = np.abs(np.asarray(ub) - refb[fft.local_slice(False)]).max()
         assert err <= 10 * tol, (name, rank, err)
         # DistArray.redistribute == a bare Transfer (reference distarray.py:298-363)
         z = B.DistArray(g.shape, dtype=g.dtype, alignment=len(g.shape) - 1)

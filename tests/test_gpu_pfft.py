@@ -230,7 +230,8 @@ class Played(object):
 
 MULTI = ['c1_c2c_16_p2', 'c3_c2c_16_p8_pencil', 'c4_r2c_16_p8_slab', 'c4_r2c_16_p8_slab_collapse',
          'c5_c2c_8x4_p8_grid42', 'uneven_r2c_12_13_14_p4', 'uneven_c2c_13_12_11_p6_axes201',
-         'uneven_c2c_7_9_p3_2d', 'c2c_4d_nested_p4', 'r2c_3d_nested_collapse_p4']
+         'uneven_c2c_7_9_p3_2d', 'c2c_4d_nested_p4', 'r2c_3d_nested_collapse_p4',
+         'pad_c2c_8_p4_3half', 'pad_r2c_8_12_10_p4_3half', 'pad_c2c_9_7_p2_mixed', 'pad_r2c_10_9_8_p1']
 
 
 @pytest.mark.parametrize('name', MULTI)
@@ -250,8 +251,42 @@ def test_all_ranks_played_on_one_gpu(B, layouts, values, name):
         assert tuple(out[r].shape) == tuple(ranks[r]['local_shape_out'])
         assert np.abs(np.asarray(out[r]) - ref[sl]).max() <= tol * max(1.0, np.abs(ref).max()), (name, r)
     back = job.backward(out)
+    refb = values[name + '__backward']      # == the input, except for padded (lossy) transforms
     for r in range(n):
-        assert np.abs(np.asarray(back[r]) - blocks[r]).max() <= 10 * tol, (name, r)
+        slin = tuple(slice(a, b) for a, b in ranks[r]['local_slice_in'])
+        assert np.abs(np.asarray(back[r]) - refb[slin]).max() <= 10 * tol, (name, r)
+
+
+SERIAL_PAD = ['spad_c_even', 'spad_c_odd', 'spad_c_first_axis', 'spad_r_even_half', 'spad_r_odd_half',
+              'spad_r_evenhalf2', 'spad_r_first_axis']
+
+
+@pytest.mark.parametrize('name', SERIAL_PAD)
+def test_padded_serial_stage_vs_reference(B, layouts, values, name):
+    """libfft.FFT(padding=...) on the device against the reference's own outputs
+    (fixtures made by oracle/make_golden.py from the unmodified libfft.FFT): the
+    truncation / zero padding and its Nyquist rule (libfft.py:263-311), complex and
+    real, odd and even extents, both normalisation switches"""
+    import pfft_oracle as O
+    meta = layouts['_' + name]
+    x, y, z = values[name + '__input'], values[name + '__forward'], values[name + '__backward']
+    f = B.FFT(meta['shape'], axes=(meta['axis'],), dtype=meta['dtype'], padding=meta['padding'])
+    assert list(f.forward.output_shape) == meta['trunc_shape']
+    u = B.fftw.aligned(meta['shape'], dtype=meta['dtype'])
+    u[...] = x
+    got = np.asarray(f.forward(u)).copy()
+    assert np.abs(got - y).max() <= 1e-12 * max(1.0, np.abs(y).max())
+    raw = np.asarray(f.forward(u, normalize=False)).copy()
+    assert np.abs(raw - y * meta['shape'][meta['axis']]).max() <= 1e-11 * max(1.0, np.abs(raw).max())
+    v = B.fftw.aligned(meta['trunc_shape'], dtype=meta['trunc_dtype'])
+    v[...] = y
+    back = np.asarray(f.backward(v)).copy()
+    assert np.abs(back - z).max() <= 1e-12 * max(1.0, np.abs(z).max())
+    # host arrays in and out, as scripts written for the reference pass them
+    out = np.zeros(meta['trunc_shape'], dtype=meta['trunc_dtype'])
+    f.forward(x, out)
+    assert np.abs(out - y).max() <= 1e-12 * max(1.0, np.abs(y).max())
+    assert np.abs(got - O.padded_stage_forward(x, meta['axis'], meta['padding'])).max() <= 1e-12
 
 
 @pytest.mark.parametrize('itemsize_dtype', ['f', 'd', 'F', 'D'])
