@@ -199,16 +199,19 @@ static int staged_default(int n, long long row_bytes) {
     switch (n) {
         case 64: return 0;
         case 128: return hostile ? 0 : 1;
-        case 256: return hostile ? 1 : 0;
-        case 512: return hostile ? 6 : 2;
-        case 1024: return 100;
+        case 256: return 102;                    // cp.async, 256-B rows, twiddles in shared memory
+        case 512: return hostile ? 105 : 2;      // profiles/r1d_sweep_opt.txt
+        case 1024: return hostile ? 100 : 102;
         case 2048: return 0;
         default: return -1;
     }
 }
 static int staged_fallback(int n) {
     switch (n) {
-        case 256: case 512: case 1024: case 2048: return 100;
+        case 256: return 102;
+        case 512: return 105;
+        case 1024: return 102;
+        case 2048: return 100;
         default: return -1;
     }
 }

@@ -93,12 +93,20 @@
 //   SPLIT   1 = the exchange buffer holds one real component at a time
 //   PS      pad period of the exchange buffer (rows narrower than 128 B need
 //           log2(first radix); 30 = none)
+//   MINB    min CTAs per SM  +  16 * OPT   (OPT bit 0: pass twiddles live in shared
+//           memory; bit 1: cp.async requests of the next tile are spread over the
+//           current tile's phases) -- fft_tma.cuh
 #define B2F_TMA_TABLE(X)                           \
     X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8)             \
+    X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8)            \
     X(128, 0, 16, 16, 30, 2, 0, 1, 16, 8)          \
     X(128, 1, 16, 8, 30, 2, 0, 1, 16, 8)           \
+    X(128, 2, 16, 16, 30, 2, 0, 17, 16, 8)         \
+    X(128, 3, 16, 8, 30, 2, 0, 17, 16, 8)          \
     X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)          \
     X(256, 1, 16, 16, 30, 2, 0, 1, 16, 16)         \
+    X(256, 2, 16, 8, 30, 2, 0, 17, 16, 16)         \
+    X(256, 3, 16, 16, 30, 2, 0, 17, 16, 16)        \
     X(512, 0, 16, 8, 3, 1, 1, 2, 8, 8, 8)          \
     X(512, 1, 32, 8, 5, 1, 1, 1, 32, 16)           \
     X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8)         \
@@ -107,12 +115,15 @@
     X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16)          \
     X(512, 6, 32, 16, 5, 1, 1, 1, 32, 16)          \
     X(512, 7, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
+    X(512, 8, 16, 8, 30, 2, 0, 17, 8, 8, 8)        \
+    X(512, 9, 32, 16, 5, 1, 1, 17, 32, 16)         \
     X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
     X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
     X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8)        \
     X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32)          \
     X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8)        \
     X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32)          \
+    X(1024, 6, 32, 8, 5, 1, 1, 17, 32, 32)         \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 // the same pipeline filled by cp.async instead of TMA (variant_tma = 100 + VAR)
@@ -123,6 +134,16 @@
     X(512, 2, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
     X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
     X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
+    X(1024, 2, 32, 8, 5, 1, 1, 17, 32, 32)         \
+    X(1024, 3, 32, 8, 5, 1, 1, 33, 32, 32)         \
+    X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32)         \
+    X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8)       \
+    X(512, 3, 32, 16, 5, 1, 1, 49, 32, 16)         \
+    X(512, 4, 16, 8, 30, 2, 0, 49, 8, 8, 8)        \
+    X(512, 5, 32, 16, 5, 1, 1, 17, 32, 16)         \
+    X(512, 6, 16, 8, 30, 2, 0, 17, 8, 8, 8)        \
+    X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16)         \
+    X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16)        \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 // real transforms (r2c / c2r of even length 2N through the N-point schedule,

@@ -158,26 +158,36 @@ static B2F_HD void load_stage(typename TF::C* v, int p, int q, const typename TF
 template <class TF, class EX, int S>
 struct TmaMid {
     using C = typename TF::C;
-    static __device__ __forceinline__ void run(C* v, int p, int q, typename EX::X* xbuf, const C* __restrict__ tw, bool split) {
+    // hook(k): called at two points of the first exchange (k = 2, 3) so that the
+    // loader can spread its requests over the tile's lifetime
+    template <class HOOK>
+    static __device__ __forceinline__ void run(C* v, int p, int q, typename EX::X* xbuf, const C* __restrict__ tw,
+                                               bool split, HOOK&& hook) {
         if constexpr (S < TF::NPASS) {
             // exchange between pass S-1 and pass S (the caller's values are post pass S-1)
             EX::template put<S - 1>(v, p, q, xbuf, 0);
             __syncthreads();
             EX::template get<S>(v, p, q, xbuf, 0);
+            if constexpr (S == 1) hook(2);
             if (split) {
                 __syncthreads();
                 EX::template put<S - 1>(v, p, q, xbuf, 1);
                 __syncthreads();
                 EX::template get<S>(v, p, q, xbuf, 1);
             }
+            if constexpr (S == 1) hook(3);
             TF::template twiddle_dft<S>(v, q, tw);
             if constexpr (S + 1 < TF::NPASS) __syncthreads();   // buffer is rewritten by the next exchange
-            TmaMid<TF, EX, S + 1>::run(v, p, q, xbuf, tw, split);
+            TmaMid<TF, EX, S + 1>::run(v, p, q, xbuf, tw, split, hook);
         }
     }
 };
 
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP, bool PEER>
+// OPT bit 0: pass twiddles are copied to shared memory once per CTA (the L1 left
+// beside a ~200 KiB carve-out does not keep them); bit 1: the cp.async loader
+// spreads the next tile's requests over the current tile's phases instead of
+// issuing them in one burst (LSU queue pressure)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP, bool PEER, int OPT>
 __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const TmaParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
@@ -194,6 +204,12 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
     const int q = TF::slot_of(tid);
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
     const long long first = blockIdx.x, step = gridDim.x;
+    if constexpr ((OPT & 1) != 0) {
+        C* tws = reinterpret_cast<C*>(b2f_tma_smem + (size_t)STAGES * TILE_BYTES + EX::bytes);
+        for (int k = tid; k < RAD::tw_total(); k += TF::THREADS) tws[k] = tw[k];
+        tw = tws;
+        __syncthreads();
+    }
 
     if (LOADER == 0) {
         if (tid == 0) {
@@ -215,21 +231,28 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
     };
     // cp.async flavour: every thread copies the E elements it will read back
     // (row q + e*TP, column p); one commit group per tile slot, empty or not
-    auto issue_cpa = [&](long long t, int s) {
+    // part k of 4 (or everything when part < 0); the commit closes the tile's group
+    auto issue_cpa_part = [&](long long t, int s, int part) {
         if (t < prm.ntiles) {
             const long long o = t / prm.tiles_per_outer;
             const long long i = (t - o * prm.tiles_per_outer) * P + p;
             const bool ok = i < prm.inner;
             const C* src = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + (ok ? i : 0);
             C* dst = stages + (size_t)s * N * P + p;
+            constexpr int Q4 = E >= 4 ? E / 4 : E;
+            const int e0 = part < 0 ? 0 : part * Q4, e1 = part < 0 ? E : (part == 3 || E < 4 ? E : e0 + Q4);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int row = q + e * TF::TP;
-                cp_async_elem<(int)sizeof(C)>(dst + row * P, src + (long long)row * prm.in_nstride, ok);
+                if (e >= e0 && e < e1) {
+                    const int row = q + e * TF::TP;
+                    cp_async_elem<(int)sizeof(C)>(dst + row * P, src + (long long)row * prm.in_nstride, ok);
+                }
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (part < 0 || part == 3) asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto issue_cpa = [&](long long t, int s) { issue_cpa_part(t, s, -1); };
+    constexpr bool SPREAD = LOADER == 1 && (OPT & 2) != 0 && E >= 4 && TF::NPASS > 1;
     if (LOADER == 0) {
         if (tid == 0) {
 #pragma unroll
@@ -258,13 +281,19 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         }
         load_stage<TF>(v, p, q, stages + (size_t)s * N * P, SWAP);
         __syncthreads();   // every thread has read stage s (and finished with the exchange buffer of the previous tile)
+        const long long tn = t + (long long)STAGES * step;
         if (LOADER == 0) {
-            if (tid == 0 && t + (long long)STAGES * step < prm.ntiles) issue(t + (long long)STAGES * step, s);
+            if (tid == 0 && tn < prm.ntiles) issue(tn, s);
+        } else if (SPREAD) {
+            issue_cpa_part(tn, s, 0);
         } else {
-            issue_cpa(t + (long long)STAGES * step, s);
+            issue_cpa(tn, s);
         }
         TF::template twiddle_dft<0>(v, q, tw);
-        TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT);
+        if (SPREAD) issue_cpa_part(tn, s, 1);
+        TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT, [&](int k) {
+            if (SPREAD) issue_cpa_part(tn, s, k);
+        });
         if constexpr (PEER) {
             long long part = 0, rest = 0;
             if (valid) prm.peer.locate(o, i, &part, &rest);
@@ -279,31 +308,31 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
     }
 }
 
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
+__global__ void __launch_bounds__((N / E) * P, (MO & 15))
 fft_tma_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, false>(&map_in, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, false>(&map_in, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, false, (MO >> 4)>(&map_in, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, false, (MO >> 4)>(&map_in, prm);
 }
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
+__global__ void __launch_bounds__((N / E) * P, (MO & 15))
 fft_tma_peer_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, true>(&map_in, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, true>(&map_in, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, true, (MO >> 4)>(&map_in, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, true, (MO >> 4)>(&map_in, prm);
 }
 
 // the same pipeline with the cp.async loader (no descriptor)
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
+__global__ void __launch_bounds__((N / E) * P, (MO & 15))
 fft_cpa_kernel(const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, false>(nullptr, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, false>(nullptr, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, false, (MO >> 4)>(nullptr, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, false, (MO >> 4)>(nullptr, prm);
 }
-template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MINB>
-__global__ void __launch_bounds__((N / E) * P, MINB)
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
+__global__ void __launch_bounds__((N / E) * P, (MO & 15))
 fft_cpa_peer_kernel(const TmaParams prm) {
-    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, true>(nullptr, prm);
-    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, true>(nullptr, prm);
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, true, (MO >> 4)>(nullptr, prm);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, true, (MO >> 4)>(nullptr, prm);
 }
 
 #endif  // __CUDACC__

@@ -51,7 +51,7 @@ static cudaError_t launch_cpa_one(const TmaStep& st, cudaStream_t stream) {
     auto kern = peer ? fft_cpa_peer_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>
                      : fft_cpa_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
     constexpr size_t tile_bytes = sizeof(cplx<T>) * (size_t)N * P;
-    constexpr size_t smem = STAGES * tile_bytes + EX::bytes;
+    constexpr size_t smem = STAGES * tile_bytes + EX::bytes + (((MINB >> 4) & 1) ? sizeof(cplx<T>) * (size_t)RAD::tw_total() : 0);
     static_assert(smem <= 227 * 1024, "tile does not fit shared memory");
     static int ctas_cache[2] = {0, 0};   // per instantiation and flavour
     int& ctas_per_sm = ctas_cache[peer];
@@ -85,7 +85,7 @@ static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
     auto kern = peer ? fft_tma_peer_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>
                      : fft_tma_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
     constexpr size_t tile_bytes = sizeof(cplx<T>) * (size_t)N * P;
-    constexpr size_t smem = STAGES * tile_bytes + EX::bytes;
+    constexpr size_t smem = STAGES * tile_bytes + EX::bytes + (((MINB >> 4) & 1) ? sizeof(cplx<T>) * (size_t)RAD::tw_total() : 0);
     static_assert(smem <= 227 * 1024, "tile does not fit shared memory");
     static int ctas_cache[2] = {0, 0};   // per instantiation and flavour
     int& ctas_per_sm = ctas_cache[peer];

@@ -61,7 +61,7 @@ def test_tma_staged_variants(emu, n, prec):
     """fft_tma.cuh: stage read, split / unsplit exchange, ragged last tile"""
     tol = 2e-15 if prec == 8 else 2e-6
     found = 0
-    for var in range(8):
+    for var in range(10):
         for outer, inner in ((2, 8), (1, 19)):
             for swap in (0, 1):
                 err = run_tma(emu, prec, n, var, outer, inner, swap, 1.0 / n if swap else 1.0, inplace=bool(swap))
