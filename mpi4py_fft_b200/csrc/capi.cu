@@ -199,7 +199,7 @@ static int staged_default(int n, long long row_bytes) {
     switch (n) {
         case 64: return 0;
         case 128: return hostile ? 0 : 1;
-        case 256: return 102;                    // cp.async, 256-B rows, twiddles in shared memory
+        case 256: return hostile ? 103 : 102;    // cp.async, 256-B rows, twiddles in shared memory (+ L2 prefetch)
         case 512: return hostile ? 105 : 2;      // profiles/r1d_sweep_opt.txt
         case 1024: return hostile ? 100 : 102;
         case 2048: return 0;

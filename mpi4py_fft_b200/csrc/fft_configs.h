@@ -95,7 +95,7 @@
 //           log2(first radix); 30 = none)
 //   MINB    min CTAs per SM  +  16 * OPT   (OPT bit 0: pass twiddles live in shared
 //           memory; bit 1: cp.async requests of the next tile are spread over the
-//           current tile's phases) -- fft_tma.cuh
+//           current tile's phases; bit 2: L2 prefetch of the tile after next) -- fft_tma.cuh
 #define B2F_TMA_TABLE(X)                           \
     X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8)             \
     X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8)            \
@@ -144,6 +144,9 @@
     X(512, 6, 16, 8, 30, 2, 0, 17, 8, 8, 8)        \
     X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16)         \
     X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16)        \
+    X(256, 3, 16, 16, 30, 2, 0, 81, 16, 16)        \
+    X(512, 7, 32, 16, 5, 1, 1, 81, 32, 16)         \
+    X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32)         \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 // real transforms (r2c / c2r of even length 2N through the N-point schedule,

@@ -252,6 +252,22 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         if (part < 0 || part == 3) asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto issue_cpa = [&](long long t, int s) { issue_cpa_part(t, s, -1); };
+    // OPT bit 2: pull the tile after next into L2 ahead of time.  A prefetch needs no
+    // landing buffer, so it takes the address-translation latency of rows that sit in
+    // different pages off the critical path and doubles the bytes in flight per SM.
+    auto prefetch_tile = [&](long long t) {
+        if (t < prm.ntiles) {
+            const long long o = t / prm.tiles_per_outer;
+            const long long i0 = (t - o * prm.tiles_per_outer) * P;
+            const char* base = reinterpret_cast<const char*>(reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i0);
+            constexpr int SEG = (int)(P * sizeof(C) + 127) / 128;     // 128-byte lines per row
+            for (int r = tid; r < N * SEG; r += TF::THREADS) {
+                const int row = r / SEG, seg = r - row * SEG;
+                const char* ptr = base + (long long)row * prm.in_nstride * (long long)sizeof(C) + seg * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+    };
     constexpr bool SPREAD = LOADER == 1 && (OPT & 2) != 0 && E >= 4 && TF::NPASS > 1;
     if (LOADER == 0) {
         if (tid == 0) {
@@ -264,6 +280,7 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         for (int s = 0; s < STAGES; ++s) issue_cpa(first + s * step, s);
     }
 
+    if constexpr ((OPT & 4) != 0) prefetch_tile(first + (long long)STAGES * step);
     int s = 0;
     uint32_t parity = 0;
     for (long long t = first; t < prm.ntiles; t += step) {
@@ -289,6 +306,7 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         } else {
             issue_cpa(tn, s);
         }
+        if constexpr ((OPT & 4) != 0) prefetch_tile(tn + step);
         TF::template twiddle_dft<0>(v, q, tw);
         if (SPREAD) issue_cpa_part(tn, s, 1);
         TmaMid<TF, EX, 1>::run(v, p, q, xbuf, tw, SPLIT, [&](int k) {

@@ -167,7 +167,7 @@ def test_tma_staged_strided_c2c(B, n, dt):
         _lib.set_option('strided_engine', 2)
         _lib.set_option('variant_strict', 1)
         served = 0
-        for variant in list(range(10)) + list(range(100, 107)):     # 100.. = cp.async-loaded flavour
+        for variant in list(range(10)) + list(range(100, 108)):     # 100.. = cp.async-loaded flavour
             _lib.set_option('variant_tma', variant)
             for shape in shapes:
                 axis = shape.index(n)
