@@ -200,6 +200,8 @@ static int staged_default(int n, long long row_bytes) {
         case 64: return 0;
         case 128: return hostile ? 0 : 1;
         case 256: return hostile ? 103 : 102;    // cp.async, 256-B rows, twiddles in shared memory (+ L2 prefetch)
+        case 384: return hostile ? 101 : -1;     // register path is as fast on friendly strides
+        case 768: return 100;
         case 512: return hostile ? 105 : 2;      // profiles/r1d_sweep_opt.txt
         case 1024: return hostile ? 100 : 102;
         case 2048: return 0;
@@ -208,6 +210,8 @@ static int staged_default(int n, long long row_bytes) {
 }
 static int staged_fallback(int n) {
     switch (n) {
+        case 384: return 101;
+        case 768: return 100;
         case 256: return 102;
         case 512: return 105;
         case 1024: return 102;
@@ -217,6 +221,10 @@ static int staged_fallback(int n) {
 }
 
 static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
+// 3 * 2^k, 3 <= n <= 6144: served by the radix-3/6/12/24 schedules
+static bool is_mixed(long long n) { return n >= 3 && n <= B2F_MIXED_MAX_N && n % 3 == 0 && (n == 3 || is_pow2(n / 3)); }
+// lengths with a Stockham kernel instance
+static bool is_stockham(long long n) { return (is_pow2(n) && n <= B2F_POW2_MAX_N) || is_mixed(n); }
 
 // does the chirp-z convolution of this transform fit the largest tile (M <= 8192)?
 static bool chirp_fits(int kind, long long n) {
@@ -254,11 +262,11 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     s.dst = dst;
     // logical transform length: the real side for r2c / c2r
     const long long n = (kind == B2F_C2R) ? s.n_out : s.n_in;
-    if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_pow2(n) && n <= B2F_POW2_MAX_N) {
+    if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_stockham(n) && option("stockham", 1)) {
         s.type = STEP_POW2;
         s.swap = (kind == B2F_BACKWARD);
-    } else if ((kind == B2F_R2C || kind == B2F_C2R) && is_pow2(n) && n >= 4 && n <= 2 * B2F_POW2_MAX_N &&
-               option("real_engine", 0) != 1) {
+    } else if ((kind == B2F_R2C || kind == B2F_C2R) && n >= 4 && n % 2 == 0 && is_stockham(n / 2) &&
+               option("real_engine", 0) != 1 && option("stockham", 1)) {
         // even-length real transform = n/2-point complex Stockham + split/merge pass
         s.type = STEP_REAL;
         if ((kind == B2F_R2C ? s.n_out : s.n_in) != n / 2 + 1) {
@@ -284,7 +292,8 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     } else {
         if (n > B2F_GENERIC_MAX_N) {
             set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
-                      " is not supported by this build (power-of-two c2c up to 8192, any kind up to 4096)");
+                      " is not supported by this build (c2c: 2^k <= 8192 and 3*2^k <= 6144; r2c/c2r: twice those; "
+                      "any other length / kind up to 4096)");
             return B2F_EUNSUPPORTED;
         }
         s.type = STEP_GENERIC;
@@ -461,6 +470,9 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             }
             int var = strided ? variant_s : variant_c;
             auto launch = [&](int v) -> cudaError_t {
+                if (is_mixed(n))
+                    return pl->precision == 8 ? launch_pow2_mixed_f64(n, v, strided, prm, s.outer, st)
+                                              : launch_pow2_mixed_f32(n, v, strided, prm, s.outer, st);
                 if (pl->precision == 8) {
                     if (n <= 256) return launch_pow2_small_f64(n, v, strided, prm, s.outer, st);
                     if (n <= 1024) return launch_pow2_mid_f64(n, v, strided, prm, s.outer, st);

@@ -87,6 +87,36 @@
     X(4096, 0, 16, 2, 4, 1, 16, 16, 16)   \
     X(8192, 0, 16, 1, 4, 1, 16, 8, 8, 8)
 
+// lengths 3 * 2^k (the sizes a 3/2-rule padded solver produces): radices from
+// {3, 4, 6, 8, 12, 24}, 24 points per thread above n = 24
+#define B2F_CONTIG_MIXED(X)               \
+    X(3, 0, 3, 128, 30, 1, 3)             \
+    X(6, 0, 6, 64, 30, 1, 6)              \
+    X(12, 0, 12, 64, 30, 1, 12)           \
+    X(24, 0, 24, 64, 30, 1, 24)           \
+    X(48, 0, 24, 32, 3, 1, 8, 6)          \
+    X(96, 0, 24, 32, 3, 1, 12, 8)         \
+    X(192, 0, 24, 16, 3, 1, 24, 8)        \
+    X(384, 0, 24, 8, 3, 1, 6, 8, 8)       \
+    X(768, 0, 24, 4, 3, 1, 12, 8, 8)      \
+    X(1536, 0, 24, 2, 3, 1, 24, 8, 8)     \
+    X(3072, 0, 24, 1, 3, 1, 6, 8, 8, 8)   \
+    X(6144, 0, 24, 1, 3, 1, 24, 8, 8, 4)
+
+#define B2F_STRIDED_MIXED(X)              \
+    X(3, 0, 3, 128, 30, 1, 3)             \
+    X(6, 0, 6, 64, 30, 1, 6)              \
+    X(12, 0, 12, 64, 30, 1, 12)           \
+    X(24, 0, 24, 64, 30, 1, 24)           \
+    X(48, 0, 24, 32, 30, 1, 8, 6)         \
+    X(96, 0, 24, 32, 30, 1, 12, 8)        \
+    X(192, 0, 24, 16, 30, 1, 24, 8)       \
+    X(384, 0, 24, 8, 30, 1, 6, 8, 8)      \
+    X(768, 0, 24, 8, 30, 1, 12, 8, 8)     \
+    X(1536, 0, 24, 8, 30, 1, 24, 8, 8)    \
+    X(3072, 0, 24, 4, 30, 1, 6, 8, 8, 8)  \
+    X(6144, 0, 24, 2, 30, 1, 24, 8, 8, 4)
+
 // TMA-staged strided kernels (fft_tma.cuh):
 //   X(N, VAR, E, P, PS, STAGES, SPLIT, MINB, radices...)
 //   STAGES  shared-memory stages the TMA engine fills ahead of the compute
@@ -145,13 +175,18 @@
     X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16)         \
     X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16)        \
     X(256, 3, 16, 16, 30, 2, 0, 81, 16, 16)        \
+    X(192, 0, 24, 16, 30, 2, 0, 17, 24, 8)         \
+    X(384, 0, 24, 8, 30, 2, 0, 17, 6, 8, 8)        \
+    X(384, 1, 24, 16, 30, 1, 0, 17, 6, 8, 8)       \
+    X(768, 0, 24, 8, 30, 1, 0, 17, 12, 8, 8)       \
+    X(768, 1, 24, 8, 3, 1, 1, 17, 12, 8, 8)        \
     X(512, 7, 32, 16, 5, 1, 1, 81, 32, 16)         \
     X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32)         \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 // real transforms (r2c / c2r of even length 2N through the N-point schedule,
 // fft_pow2.cuh fft_real_kernel):  X(N, E, P, PS, MINB, radices...), one row per N
-#define B2F_REAL_CONTIG(X)               \
+#define B2F_REAL_CONTIG_POW2(X)          \
     X(2, 2, 128, 30, 1, 2)               \
     X(4, 4, 128, 30, 1, 4)               \
     X(8, 8, 64, 30, 1, 8)                \
@@ -166,7 +201,21 @@
     X(4096, 16, 1, 4, 1, 16, 16, 16)     \
     X(8192, 16, 1, 4, 1, 16, 8, 8, 8)
 
-#define B2F_REAL_STRIDED(X)              \
+#define B2F_REAL_CONTIG_MIXED(X)         \
+    X(3, 3, 128, 30, 1, 3)               \
+    X(6, 6, 64, 30, 1, 6)                \
+    X(12, 12, 64, 30, 1, 12)             \
+    X(24, 24, 64, 30, 1, 24)             \
+    X(48, 24, 32, 3, 1, 8, 6)            \
+    X(96, 24, 32, 3, 1, 12, 8)           \
+    X(192, 24, 16, 3, 1, 24, 8)          \
+    X(384, 24, 8, 3, 1, 6, 8, 8)         \
+    X(768, 24, 4, 3, 1, 12, 8, 8)        \
+    X(1536, 24, 2, 3, 1, 24, 8, 8)       \
+    X(3072, 24, 1, 3, 1, 6, 8, 8, 8)     \
+    X(6144, 24, 1, 3, 1, 24, 8, 8, 4)
+
+#define B2F_REAL_STRIDED_POW2(X)         \
     X(2, 2, 128, 30, 1, 2)               \
     X(4, 4, 128, 30, 1, 4)               \
     X(8, 8, 64, 30, 1, 8)                \
@@ -181,7 +230,24 @@
     X(4096, 16, 2, 4, 1, 16, 16, 16)     \
     X(8192, 16, 1, 4, 1, 16, 8, 8, 8)
 
-#define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X)
-#define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X)
+#define B2F_REAL_STRIDED_MIXED(X)        \
+    X(3, 3, 128, 30, 1, 3)               \
+    X(6, 6, 64, 30, 1, 6)                \
+    X(12, 12, 64, 30, 1, 12)             \
+    X(24, 24, 64, 30, 1, 24)             \
+    X(48, 24, 32, 30, 1, 8, 6)           \
+    X(96, 24, 32, 30, 1, 12, 8)          \
+    X(192, 24, 16, 30, 1, 24, 8)         \
+    X(384, 24, 8, 30, 1, 6, 8, 8)        \
+    X(768, 24, 8, 30, 1, 12, 8, 8)       \
+    X(1536, 24, 8, 30, 1, 24, 8, 8)      \
+    X(3072, 24, 4, 30, 1, 6, 8, 8, 8)    \
+    X(6144, 24, 2, 30, 1, 24, 8, 8, 4)
+
+#define B2F_REAL_CONTIG(X) B2F_REAL_CONTIG_POW2(X) B2F_REAL_CONTIG_MIXED(X)
+#define B2F_REAL_STRIDED(X) B2F_REAL_STRIDED_POW2(X) B2F_REAL_STRIDED_MIXED(X)
+#define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X) B2F_CONTIG_MIXED(X)
+#define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X) B2F_STRIDED_MIXED(X)
 
 #define B2F_POW2_MAX_N 8192
+#define B2F_MIXED_MAX_N 6144

@@ -71,6 +71,24 @@ B2F_HD cplx<T> mul_w32(cplx<T> a, int s) {
 // Decimation in time by two; all indices are compile-time constants after
 // unrolling so v/e/o live in registers.
 // ---------------------------------------------------------------------------
+// multiply by W_24^s = exp(-2*pi*i*s/24), s a loop constant in [0,12): the
+// butterfly twiddles of the radices 6, 12 and 24 (lengths 3 * 2^k)
+template <class T>
+B2F_HD cplx<T> mul_w24(cplx<T> a, int s) {
+    constexpr double C[12] = {
+        1.0, 0.96592582628906828675, 0.86602540378443864676, 0.70710678118654752440,
+        0.5, 0.25881904510252076235, 0.0, -0.25881904510252076235,
+        -0.5, -0.70710678118654752440, -0.86602540378443864676, -0.96592582628906828675};
+    constexpr double S[12] = {
+        0.0, 0.25881904510252076235, 0.5, 0.70710678118654752440,
+        0.86602540378443864676, 0.96592582628906828675, 1.0, 0.96592582628906828675,
+        0.86602540378443864676, 0.70710678118654752440, 0.5, 0.25881904510252076235};
+    if (s == 0) return a;
+    if (s == 6) return mul_mi(a);
+    const T c = (T)C[s], sn = (T)S[s];
+    return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+}
+
 template <int R, class T>
 struct DftReg {
     static B2F_HD void run(cplx<T>* v) {
@@ -84,10 +102,24 @@ struct DftReg {
         DftReg<R / 2, T>::run(o);
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
-            cplx<T> t = mul_w32(o[k], k * (32 / R));
+            cplx<T> t;
+            if constexpr ((R & (R - 1)) == 0) t = mul_w32(o[k], k * (32 / R));
+            else t = mul_w24(o[k], k * (24 / R));
             v[k] = e[k] + t;
             v[k + R / 2] = e[k] - t;
         }
+    }
+};
+template <class T>
+struct DftReg<3, T> {
+    static B2F_HD void run(cplx<T>* v) {
+        const T h = (T)0.86602540378443864676;   // sin(2*pi/3)
+        const cplx<T> s = v[1] + v[2], d = v[1] - v[2];
+        const cplx<T> m = {v[0].x - (T)0.5 * s.x, v[0].y - (T)0.5 * s.y};
+        const cplx<T> r = {h * d.y, -h * d.x};   // -i * h * d
+        v[0] = v[0] + s;
+        v[1] = m + r;
+        v[2] = m - r;
     }
 };
 template <class T>
@@ -301,7 +333,7 @@ struct TileFFT {
     template <int R, int Ns>
     static B2F_HD void apply_twiddles(C* v, const C* __restrict__ t) {
 #if B2F_TW_POW2
-        if constexpr (R <= 4) {
+        if constexpr (R <= 4 || (R & (R - 1)) != 0) {
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = cmul(v[r], t[(r - 1) * Ns]);
         } else {
@@ -342,6 +374,7 @@ struct TileFFT {
         constexpr int NB = E / R;
         static_assert(E % R == 0, "radix must divide E");
         static_assert(R <= 32, "radix above 32 is not implemented");
+        static_assert((R & (R - 1)) == 0 || R == 3 || R == 6 || R == 12 || R == 24, "radix must be 2^a or 3 * 2^a");
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if (S > 0) {
@@ -457,7 +490,7 @@ struct TileFFT {
         for (int e = 0; e < E; ++e) {
             const int k = q + e * TP;
             const C a = smem[SI::at(p, k)];
-            C b = smem[SI::at(p, (N - k) & (N - 1))];
+            C b = smem[SI::at(p, k == 0 ? 0 : N - k)];
             b.y = -b.y;
             const C sm = a + b, d = a - b;
             const C t = cmul(w[k], d);

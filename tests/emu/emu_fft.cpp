@@ -578,9 +578,9 @@ static int emu_chirp_one(const ChirpParams& prm_in, long long outer) {
 template <class T>
 static int emu_chirp_dispatch(int m, bool strided, const ChirpParams& prm, long long outer) {
     if (strided) {
-        B2F_REAL_STRIDED(EMU_CHIRP_STRIDED)
+        B2F_REAL_STRIDED_POW2(EMU_CHIRP_STRIDED)
     } else {
-        B2F_REAL_CONTIG(EMU_CHIRP_CONTIG)
+        B2F_REAL_CONTIG_POW2(EMU_CHIRP_CONTIG)
     }
     return -1;
 }

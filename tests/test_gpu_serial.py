@@ -67,11 +67,13 @@ def test_docstring_vectors_on_device(B):
     assert np.isclose(dct.get_normalization(), 1.0 / 8)
 
 
-@pytest.mark.parametrize('n', [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize('n', [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192,
+                               3, 6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144])
 @pytest.mark.parametrize('dt', ['D', 'F'])
 def test_stockham_pow2_c2c(B, n, dt):
     """contiguous axis, strided axes with ragged tiles, forward/backward, fused
-    normalisation, in place -- every variant of fft_configs.h"""
+    normalisation, in place -- every variant of fft_configs.h; lengths 2^k and
+    3 * 2^k (radices 3, 6, 12, 24)"""
     from mpi4py_fft_b200 import _lib
     tol = TOL[dt.lower()]
     shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 2048 else [(2, n), (n, 5)]
@@ -100,7 +102,8 @@ def test_stockham_pow2_c2c(B, n, dt):
         _lib.set_option('variant', 0)
 
 
-@pytest.mark.parametrize('n', [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize('n', [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,
+                               6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144, 12288])
 @pytest.mark.parametrize('dt', ['d', 'f'])
 def test_stockham_real_transforms(B, n, dt):
     """r2c / c2r of even power-of-two length through the n/2-point Stockham kernel
@@ -152,7 +155,7 @@ def test_stockham_real_transforms(B, n, dt):
         assert relerr(bck(), x.astype('d')) < tol
 
 
-@pytest.mark.parametrize('n', [64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize('n', [64, 128, 256, 512, 1024, 2048, 192, 384, 768])
 @pytest.mark.parametrize('dt', ['D', 'F'])
 def test_tma_staged_strided_c2c(B, n, dt):
     """strided axes through the TMA-staged persistent kernel (fft_tma.cuh), every
@@ -191,7 +194,7 @@ def test_tma_staged_strided_c2c(B, n, dt):
                 assert relerr(V, ref * n) < tol, ('inplace', n, dt, variant, shape)
                 served += 1
         assert served >= 3
-        if n >= 256:
+        if n >= 256 and n & (n - 1) == 0:
             # the cp.async flavour also serves an odd inner extent (no descriptor involved)
             _lib.set_option('variant_tma', 100)
             shape = (2, n, 21)
@@ -296,7 +299,8 @@ def test_generic_lengths_c2c(B, n, dft_ref):
         p = B.fftw.fftn(U, axes=(axis,))
         y = np.asarray(p())
         assert relerr(y, np.fft.fft(z, axis=axis)) < 1e-12
-        assert ('dense-matrix' if n <= 32 else 'chirpz') in p.plan().describe()
+        expect = 'stockham' if n in (3, 6, 12, 24) else 'dense-matrix' if n <= 32 else 'chirpz'
+        assert expect in p.plan().describe()
     z = rand((n,), 'D', 1)
     U = B.fftw.aligned((n,), dtype='D')
     U[...] = z
@@ -315,6 +319,7 @@ def test_chirpz_every_kind_any_length(B, dt, dft_ref):
     tol = TOL[dt] * (5 if dt == 'f' else 1)
     cd = dt.upper()
     _lib.set_option('generic_engine', 2)
+    _lib.set_option('stockham', 0)          # 6, 12, 384, 1536 have Stockham kernels: keep them on the chirp-z path here
     try:
         for n in (5, 6, 7, 12, 13, 30, 100, 127, 384, 1000, 1536):
             for shape, axis in (((3, n), 1), ((n, 5), 0)):
@@ -359,6 +364,7 @@ def test_chirpz_every_kind_any_length(B, dt, dft_ref):
             _lib.set_option('generic_engine', 2)
     finally:
         _lib.set_option('generic_engine', 0)
+        _lib.set_option('stockham', 1)
 
 
 @pytest.mark.parametrize('backendless', [True])
