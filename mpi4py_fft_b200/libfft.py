@@ -100,7 +100,7 @@ class _Stage(object):
         if normalize is None:
             normalize = self._default_normalize
         self._planned.execute_scatter(src, work, self._owner.M if normalize else 1.0, transfer_handle,
-                                      direction, peer_ptrs)
+                                      direction, peer_ptrs, getattr(peer_ptrs, 'sync', True))
 
     def __call__(self, input_array=None, output_array=None, **kw):
         normalize = kw.pop('normalize', self._default_normalize)
@@ -197,7 +197,8 @@ class _PaddedStage(_Stage):
         Vp = own._array(own.fwd, 'out')
         pad_truncate(1, own.real_transform, own.fwd.precision, device_ptr(src), device_ptr(Vp),
                      outer, own.trunc_shape[axis], spec_shape[axis], inner, 1.0)
-        self._planned.execute_scatter(Vp, work, own.M if normalize else 1.0, transfer_handle, direction, peer_ptrs)
+        self._planned.execute_scatter(Vp, work, own.M if normalize else 1.0, transfer_handle, direction, peer_ptrs,
+                                      getattr(peer_ptrs, 'sync', True))
 
     def __call__(self, input_array=None, output_array=None, **kw):
         normalize = kw.pop('normalize', self._default_normalize)

@@ -26,6 +26,6 @@ def test_pfft_over_nccl(world, p2p):
            os.path.join(ROOT, 'tests', 'mp_worker.py')]
     env = dict(os.environ, B2F_P2P='0' if p2p == '0' else '1', B2F_FUSED='0' if p2p == 'put' else '1')
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert r.returncode == 0 and 'MULTI_OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and 'MULTI_OK' in r.stdout, r.stdout[-6000:] + r.stderr[-3000:]
     if p2p != '0':
         assert 'transfers=p2p' in r.stdout, r.stdout[-2000:]

@@ -191,6 +191,44 @@ class Played(object):
             out.append(dst)
         return out
 
+    def _stage_then_transfer(self, cur, stage_of, ti, backward):
+        """stage on every rank followed by transfer ``ti`` (None: no transfer).  In
+        ``self.mode`` 'fused' the stage's last pass stores straight into the arrays of
+        the group's ranks (b2f_execute_scatter, no ordering needed on one device:
+        every rank's launch is on the same stream); 'put' runs the put kernel;
+        'pack' moves packed segments by hand."""
+        from mpi4py_fft_b200.devarray import device_ptr
+        B = self.B
+        nxt = []
+        trs = [f.transfer[ti] for f in self.ffts] if ti is not None else None
+        direction = 1 if backward else 0
+        p2p = trs is not None and self.mode in ('fused', 'put') and trs[0].comm.Get_size() > 1
+        recv = None
+        if p2p:
+            recv = [B.fftw.aligned(t.subshapeA if backward else t.subshapeB, dtype=t.dtype, fill=0) for t in trs]
+        self.fused_count = getattr(self, 'fused_count', 0)
+        for r, f in enumerate(self.ffts):
+            st = stage_of(f)
+            dst = B.fftw.aligned(st.output_shape, dtype=st.output_dtype)
+            if p2p:
+                ptrs = [device_ptr(recv[w]) for w in trs[r].comm.ranks]
+                if self.mode == 'fused' and st.can_scatter(self.handles[r][ti], direction):
+                    st.run_scatter(cur[r], dst, None, self.handles[r][ti], direction, ptrs_sync_off(ptrs))
+                    self.fused_count += 1
+                else:
+                    st.run(cur[r], dst)
+                    self.handles[r][ti].put(direction, dst, ptrs)
+            else:
+                st.run(cur[r], dst)
+            nxt.append(dst)
+        if p2p:
+            return recv
+        if trs is not None:
+            return self._exchange(ti, nxt, backward=backward)
+        return nxt
+
+    mode = 'pack'
+
     def forward(self, blocks):
         B = self.B
         cur = []
@@ -200,32 +238,21 @@ class Played(object):
             cur.append(a)
         nst = len(self.ffts[0].xfftn)
         for i in range(nst):
-            nxt = []
-            for r, f in enumerate(self.ffts):
-                st = f.xfftn[i].forward
-                dst = B.fftw.aligned(st.output_shape, dtype=st.output_dtype)
-                st.run(cur[r], dst)
-                nxt.append(dst)
-            cur = nxt
-            if i + 1 < nst:
-                cur = self._exchange(i, cur, backward=False)
+            cur = self._stage_then_transfer(cur, lambda f: f.xfftn[i].forward, i if i + 1 < nst else None, False)
         return cur
 
     def backward(self, blocks):
-        B = self.B
         cur = list(blocks)
         nst = len(self.ffts[0].xfftn)
         for i in range(nst - 1, -1, -1):
-            nxt = []
-            for r, f in enumerate(self.ffts):
-                st = f.xfftn[i].backward
-                dst = B.fftw.aligned(st.output_shape, dtype=st.output_dtype)
-                st.run(cur[r], dst)
-                nxt.append(dst)
-            cur = nxt
-            if i > 0:
-                cur = self._exchange(i - 1, cur, backward=True)
+            cur = self._stage_then_transfer(cur, lambda f: f.xfftn[i].backward, i - 1 if i > 0 else None, True)
         return cur
+
+
+class ptrs_sync_off(list):
+    """peer pointer list that tells _Stage.run_scatter to skip the group barriers
+    (all ranks of the job share one stream in these tests)"""
+    sync = False
 
 
 MULTI = ['c1_c2c_16_p2', 'c3_c2c_16_p8_pencil', 'c4_r2c_16_p8_slab', 'c4_r2c_16_p8_slab_collapse',
@@ -234,14 +261,19 @@ MULTI = ['c1_c2c_16_p2', 'c3_c2c_16_p8_pencil', 'c4_r2c_16_p8_slab', 'c4_r2c_16_
          'pad_c2c_8_p4_3half', 'pad_r2c_8_12_10_p4_3half', 'pad_c2c_9_7_p2_mixed', 'pad_r2c_10_9_8_p1']
 
 
+@pytest.mark.parametrize('mode', ['pack', 'put', 'fused'])
 @pytest.mark.parametrize('name', MULTI)
-def test_all_ranks_played_on_one_gpu(B, layouts, values, name):
+def test_all_ranks_played_on_one_gpu(B, layouts, values, name, mode):
+    """every golden multi-rank case with all its ranks on one device, through the
+    three implementations of the redistribution (pack/unpack by hand, put kernel,
+    stage fused with the redistribution)"""
     case = layouts[name]
     n = case['meta']['nranks']
     kw = case_kwargs(case['meta'])
     g = values[name + '__input']
     tol = TOL[g.dtype.char.lower()]
     job = Played(B, n, kw)
+    job.mode = mode
     ranks = case['ranks']
     blocks = [np.ascontiguousarray(g[tuple(slice(a, b) for a, b in ranks[r]['local_slice_in'])]) for r in range(n)]
     out = job.forward(blocks)
