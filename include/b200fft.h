@@ -188,6 +188,23 @@ B2F_API int b2f_plan_can_scatter(b2f_plan plan, b2f_transfer t, int direction);
 B2F_API int b2f_execute_scatter(b2f_plan plan, const void *d_in, void *d_work, double scale,
                         b2f_transfer t, int direction, void *const *peer_dst, int sync, void *stream);
 
+/* ---- pipelining a redistribution with the stage that consumes it ------------
+ * Partial launches of a one-axis Stockham stage, so that the producing stage can
+ * store chunk c into the peers' windows while the consuming stage already
+ * transforms chunk c-1 (two streams, an exit barrier per chunk):
+ *   mode 1: inner indices [begin, begin+count) of every pencil row; view_outer > 0
+ *           re-views the block as view_outer rows view_ostride elements apart (a
+ *           range of the last array axis when other axes follow the transformed one)
+ *   mode 2: outer indices [begin, begin+count)
+ * grid_cap limits the persistent grid (SMs) so that two stages share the GPU.
+ * sync_flags of the scatter form: bit 0 = group barrier before, bit 1 = after.   */
+B2F_API int b2f_execute_chunk(b2f_plan plan, const void *d_in, void *d_out, double scale,
+                      int mode, int64_t begin, int64_t count, int64_t view_outer, int64_t view_ostride,
+                      int grid_cap, void *stream);
+B2F_API int b2f_execute_scatter_chunk(b2f_plan plan, const void *d_in, double scale,
+                      b2f_transfer t, int direction, void *const *peer_dst, int sync_flags,
+                      int mode, int64_t begin, int64_t count, int grid_cap, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -411,6 +411,16 @@ int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* 
     return run_plan(pl, d_in, d_out, scale, (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }
 
+int b2f_execute_chunk(b2f_plan pl, const void* d_in, void* d_out, double scale, int mode, int64_t begin, int64_t count,
+                      int64_t view_outer, int64_t view_ostride, int grid_cap, void* stream) {
+    if (!pl || !d_in || !d_out) {
+        set_error("b2f_execute_chunk: null plan or buffer");
+        return B2F_EINVAL;
+    }
+    ChunkSpec ch{mode, begin, count, view_outer, view_ostride, grid_cap};
+    return run_plan(pl, d_in, d_out, scale, (cudaStream_t)stream, nullptr, nullptr, nullptr, &ch);
+}
+
 }  // extern "C"
 
 namespace b2f {
@@ -431,7 +441,17 @@ bool plan_scatter_info(b2f_plan pl, int* axis, long long* n, int* precision, con
 // arrays (fused redistribution) and `before_last(ctx)` is enqueued right before
 // it (the group barrier that says the peers' windows may be overwritten).
 int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStream_t st, const PeerStore* peer_last,
-             int (*before_last)(void*, cudaStream_t), void* ctx) {
+             int (*before_last)(void*, cudaStream_t), void* ctx, const ChunkSpec* chunk) {
+    if (chunk && chunk->mode != 0) {
+        const Step& s0 = pl->steps.back();
+        const bool ok = pl->steps.size() == 1 && s0.type == STEP_POW2 && chunk->begin >= 0 && chunk->count >= 0 &&
+                        ((chunk->mode == 1 && s0.inner > 1 && chunk->begin + chunk->count <= s0.inner) ||
+                         (chunk->mode == 2 && chunk->begin + chunk->count <= s0.outer && chunk->view_outer == 0));
+        if (!ok) {
+            set_error("partial execution needs a one-axis Stockham stage and a range inside the block");
+            return B2F_EUNSUPPORTED;
+        }
+    }
     const int variant = (int)option("variant", 0);
     const int variant_c = (int)option("variant_contig", variant);
     const int variant_s = (int)option("variant_strided", variant);
@@ -460,6 +480,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             prm.swap = s.swap ? 1 : 0;
             const bool strided = s.inner > 1;
             const int n = (int)s.n_in;
+            long long outer = s.outer;
             if (strided) {
                 prm.in_ostride = prm.out_ostride = s.n_in * s.inner;
                 prm.in_nstride = prm.out_nstride = s.inner;
@@ -468,19 +489,41 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 prm.in_ostride = prm.out_ostride = s.n_in;
                 prm.npencils = s.outer;
             }
+            const bool part = chunk && chunk->mode != 0;
+            if (part) {
+                const long long esz = 2LL * pl->precision;
+                long long off;
+                if (chunk->mode == 2) {
+                    off = chunk->begin * prm.in_ostride;
+                    outer = chunk->count;
+                    prm.npencils = outer;
+                    prm.peer.ooff = chunk->begin;
+                } else {
+                    off = chunk->begin;
+                    prm.inner = chunk->count;
+                    prm.peer.ioff = chunk->begin;
+                    if (chunk->view_outer > 0) {
+                        outer = chunk->view_outer;
+                        prm.in_ostride = prm.out_ostride = chunk->view_ostride;
+                    }
+                }
+                prm.in = src = (const char*)src + off * esz;
+                prm.out = dst = (char*)dst + off * esz;
+                if (outer == 0 || (strided && prm.inner == 0)) continue;
+            }
             int var = strided ? variant_s : variant_c;
             auto launch = [&](int v) -> cudaError_t {
                 if (is_mixed(n))
-                    return pl->precision == 8 ? launch_pow2_mixed_f64(n, v, strided, prm, s.outer, st)
-                                              : launch_pow2_mixed_f32(n, v, strided, prm, s.outer, st);
+                    return pl->precision == 8 ? launch_pow2_mixed_f64(n, v, strided, prm, outer, st)
+                                              : launch_pow2_mixed_f32(n, v, strided, prm, outer, st);
                 if (pl->precision == 8) {
-                    if (n <= 256) return launch_pow2_small_f64(n, v, strided, prm, s.outer, st);
-                    if (n <= 1024) return launch_pow2_mid_f64(n, v, strided, prm, s.outer, st);
-                    return launch_pow2_large_f64(n, v, strided, prm, s.outer, st);
+                    if (n <= 256) return launch_pow2_small_f64(n, v, strided, prm, outer, st);
+                    if (n <= 1024) return launch_pow2_mid_f64(n, v, strided, prm, outer, st);
+                    return launch_pow2_large_f64(n, v, strided, prm, outer, st);
                 }
-                if (n <= 256) return launch_pow2_small_f32(n, v, strided, prm, s.outer, st);
-                if (n <= 1024) return launch_pow2_mid_f32(n, v, strided, prm, s.outer, st);
-                return launch_pow2_large_f32(n, v, strided, prm, s.outer, st);
+                if (n <= 256) return launch_pow2_small_f32(n, v, strided, prm, outer, st);
+                if (n <= 1024) return launch_pow2_mid_f32(n, v, strided, prm, outer, st);
+                return launch_pow2_large_f32(n, v, strided, prm, outer, st);
             };
             // strided axes: TMA-staged persistent kernel where one is built for n and
             // the layout can be described to TMA, else the register-path kernel
@@ -488,7 +531,14 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             e = cudaErrorInvalidValue;
             bool done = false;
             if (strided && engine != 1) {
-                TmaStep ts{src, dst, s.outer, s.n_in, s.inner, sc, s.swap ? 1 : 0, peer};
+                PeerStore peer_part;
+                const PeerStore* peer_arg = peer;
+                if (peer && part) {
+                    peer_part = prm.peer;
+                    peer_arg = &peer_part;
+                }
+                TmaStep ts{src, dst, outer, s.n_in, prm.inner, sc, s.swap ? 1 : 0, peer_arg,
+                           part ? prm.in_nstride : 0, part ? prm.in_ostride : 0, part ? chunk->grid_cap : 0};
                 auto staged = [&](int v) {
                     return pl->precision == 8 ? launch_tma_f64(n, v, ts, st) : launch_tma_f32(n, v, ts, st);
                 };

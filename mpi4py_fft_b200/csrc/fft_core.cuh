@@ -244,11 +244,14 @@ struct PeerStore {
     void* base[B2F_MAX_PEERS];
     long long stride;
     long long M, nD, ND, sD, Q;
+    long long ooff, ioff;   // a launch over part of the block: its pencils start at (outer, inner) = (ooff, ioff)
     int p;            // owners of the transformed axis (0 = fused store not in use)
     int q, r;         // N = p*q + r: the first r owners hold q + 1 points
     int mode;
 
     B2F_HD void locate(long long o, long long i, long long* part, long long* rest) const {
+        o += ooff;
+        i += ioff;
         if (mode == 0) {
             const long long t = o / M, m = o - t * M;
             const long long pp = t / nD, i1 = t - pp * nD;

@@ -19,6 +19,7 @@ TensorMapEncodeFn tensor_map_encoder();   // capi.cu
 template <class T>
 static bool tma_can_serve(const TmaStep& st) {
     const size_t esz = 2 * sizeof(T);
+    if (st.pitch || st.ostride) return false;          // partial launches go through the cp.async flavour
     if (((uintptr_t)st.in & 15) || ((uintptr_t)st.out & 15)) return false;
     if ((st.inner * esz) % 16) return false;
     if (2 * st.inner >= (1LL << 32) || st.outer >= (1LL << 32)) return false;
@@ -27,12 +28,14 @@ static bool tma_can_serve(const TmaStep& st) {
 }
 
 static inline void fill_params(TmaParams& prm, const TmaStep& st, int P) {
+    const long long pitch = st.pitch ? st.pitch : st.inner;
+    const long long ostride = st.ostride ? st.ostride : st.n * pitch;
     prm.in = st.in;
-    prm.in_ostride = st.n * st.inner;
-    prm.in_nstride = st.inner;
+    prm.in_ostride = ostride;
+    prm.in_nstride = pitch;
     prm.out = st.out;
-    prm.out_ostride = st.n * st.inner;
-    prm.out_nstride = st.inner;
+    prm.out_ostride = ostride;
+    prm.out_nstride = pitch;
     prm.inner = st.inner;
     prm.tiles_per_outer = (st.inner + P - 1) / P;
     prm.ntiles = st.outer * prm.tiles_per_outer;
@@ -71,6 +74,7 @@ static cudaError_t launch_cpa_one(const TmaStep& st, cudaStream_t stream) {
     if (!prm.tw) return cudaErrorMemoryAllocation;
     if (prm.ntiles <= 0) return cudaSuccess;
     long long grid = (long long)sm_count() * ctas_per_sm;
+    if (st.grid_cap > 0 && grid > (long long)st.grid_cap * ctas_per_sm) grid = (long long)st.grid_cap * ctas_per_sm;
     if (grid > prm.ntiles) grid = prm.ntiles;
     kern<<<(unsigned)grid, TF::THREADS, smem, stream>>>(prm);
     count_launch();
@@ -117,6 +121,7 @@ static cudaError_t launch_tma_one(const TmaStep& st, cudaStream_t stream) {
     if (!prm.tw) return cudaErrorMemoryAllocation;
     if (prm.ntiles <= 0) return cudaSuccess;
     long long grid = (long long)sm_count() * ctas_per_sm;
+    if (st.grid_cap > 0 && grid > (long long)st.grid_cap * ctas_per_sm) grid = (long long)st.grid_cap * ctas_per_sm;
     if (grid > prm.ntiles) grid = prm.ntiles;
     kern<<<(unsigned)grid, TF::THREADS, smem, stream>>>(map, prm);
     count_launch();

@@ -44,6 +44,9 @@ struct TmaStep {
     double scale;
     int swap;
     const PeerStore* peer;   // non-null: the last pass stores into the owners' arrays
+    long long pitch;         // elements between consecutive points of a pencil (0: = inner)
+    long long ostride;       // elements between consecutive outer indices (0: = n * pitch)
+    int grid_cap;            // persistent grid limit (0: every SM) -- lets two stages share the GPU
 };
 cudaError_t launch_tma_f64(int n, int var, const TmaStep& st, cudaStream_t stream);
 cudaError_t launch_tma_f32(int n, int var, const TmaStep& st, cudaStream_t stream);
@@ -52,9 +55,21 @@ int sm_count();   // SMs of the current device (cached)
 }  // namespace b2f
 struct b2f_plan_s;
 namespace b2f {
+// A launch over part of a one-axis stage, so that the stage feeding a redistribution
+// and the stage consuming it can be pipelined chunk by chunk:
+//   mode 1: inner indices [begin, begin+count) of every pencil row; with view_outer > 0
+//           the block is re-viewed as view_outer rows view_ostride elements apart
+//           (a range of the LAST array axis when other axes follow the transformed one)
+//   mode 2: outer indices [begin, begin+count)
+struct ChunkSpec {
+    int mode;
+    long long begin, count;
+    long long view_outer, view_ostride;
+    int grid_cap;
+};
 // plan execution with an optional fused peer store in the last step (capi.cu)
 int run_plan(b2f_plan_s* pl, const void* d_in, void* d_out, double scale, cudaStream_t st, const PeerStore* peer_last,
-             int (*before_last)(void*, cudaStream_t), void* ctx);
+             int (*before_last)(void*, cudaStream_t), void* ctx, const ChunkSpec* chunk = nullptr);
 // last step of a plan: false unless it is a Stockham step (the only kind that can scatter)
 bool plan_scatter_info(b2f_plan_s* pl, int* axis, long long* n, int* precision, const long long** out_shape, int* ndims);
 

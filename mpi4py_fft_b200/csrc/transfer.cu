@@ -599,8 +599,9 @@ static int build_peer_store(b2f_transfer t, int direction, b2f_plan plan, void* 
 
 static int barrier_hook(void* ctx, cudaStream_t st) { return group_barrier((b2f_comm)ctx, st); }
 
-int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t, int direction,
-                        void* const* peer_dst, int sync, void* stream) {
+static int execute_scatter_impl(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t,
+                                int direction, void* const* peer_dst, int sync_flags, const ChunkSpec* chunk,
+                                void* stream) {
     if (!plan || !d_in || !t || !peer_dst || (direction != 0 && direction != 1)) {
         set_error("b2f_execute_scatter: bad arguments");
         return B2F_EINVAL;
@@ -609,8 +610,9 @@ int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double sc
     int rc = build_peer_store(t, direction, plan, peer_dst, &ps);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fence = sync && t->nranks > 1;
-    if (fence) {
+    const bool multi = t->nranks > 1;
+    const bool enter = multi && (sync_flags & 1), leave = multi && (sync_flags & 2);
+    if (enter || leave) {
         if (!t->comm) {
             set_error("transfer was created without a communicator");
             return B2F_EINVAL;
@@ -619,9 +621,21 @@ int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double sc
     }
     // d_work receives the intermediate of a multi-axis stage; a single-step stage never touches it
     rc = run_plan(plan, d_in, d_work ? d_work : const_cast<void*>(d_in), scale, st, &ps,
-                  fence ? barrier_hook : nullptr, fence ? (void*)t->comm : nullptr);
+                  enter ? barrier_hook : nullptr, enter ? (void*)t->comm : nullptr, chunk);
     if (rc) return rc;
-    return fence ? group_barrier(t->comm, st) : B2F_OK;
+    return leave ? group_barrier(t->comm, st) : B2F_OK;
+}
+
+int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t, int direction,
+                        void* const* peer_dst, int sync, void* stream) {
+    return execute_scatter_impl(plan, d_in, d_work, scale, t, direction, peer_dst, sync ? 3 : 0, nullptr, stream);
+}
+
+int b2f_execute_scatter_chunk(b2f_plan plan, const void* d_in, double scale, b2f_transfer t, int direction,
+                              void* const* peer_dst, int sync_flags, int mode, int64_t begin, int64_t count,
+                              int grid_cap, void* stream) {
+    ChunkSpec ch{mode, begin, count, 0, 0, grid_cap};
+    return execute_scatter_impl(plan, d_in, nullptr, scale, t, direction, peer_dst, sync_flags, &ch, stream);
 }
 
 int b2f_plan_can_scatter(b2f_plan plan, b2f_transfer t, int direction) {

@@ -480,6 +480,95 @@ def test_fused_stage_and_transfer_kernels(B, dtype):
                 assert err < tol, (shape, axes, axD, p, kind, r, err)
 
 
+@pytest.mark.parametrize('dtype', ['D', 'F'])
+def test_partial_stage_launches(B, dtype):
+    """b2f_execute_chunk / b2f_execute_scatter_chunk: a one-axis stage launched in
+    pieces (ranges of the inner index, of the last array axis through a re-viewed
+    block, or of the outer index) writes exactly what the whole launch writes; the
+    scatter form stores the pieces into the owners' arrays.  These are the launches
+    the pipelined redistribution is made of."""
+    from mpi4py_fft_b200._lib import TransferHandle, Plan
+    from mpi4py_fft_b200.devarray import device_ptr
+    from mpi4py_fft_b200.pencil import _blockdist
+    dt = np.dtype(dtype)
+    prec = 8 if dtype == 'D' else 4
+    tol = 1e-12 if dtype == 'D' else 1e-5
+    for shape, axis in (((6, 64, 40), 1), ((3, 1024, 24), 1), ((5, 512), 1), ((256, 12, 40), 0), ((1024, 3, 24), 0),
+                        ((4, 384, 16), 1)):
+        x = rand(shape, dt, 5)
+        a = B.fftw.aligned(shape, dtype=dt)
+        a[...] = x
+        ref = np.fft.fft(x.astype('D'), axis=axis)
+        plan = Plan(shape, shape, (axis,), [-1], prec)
+        outer = int(np.prod(shape[:axis]))
+        inner = int(np.prod(shape[axis + 1:]))
+        last = shape[-1]
+        # outer ranges
+        if outer > 1:
+            out = B.fftw.aligned(shape, dtype=dt, fill=0)
+            cuts = [0, outer // 2, outer]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                plan.execute_chunk(device_ptr(a), device_ptr(out), 1.0, 2, lo, hi - lo)
+            assert relerr(out, ref) < tol, ('outer', shape)
+        if inner > 1:
+            # inner ranges
+            out = B.fftw.aligned(shape, dtype=dt, fill=0)
+            cuts = [0, inner // 3, inner // 3 + 5, inner]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                plan.execute_chunk(device_ptr(a), device_ptr(out), 1.0, 1, lo, hi - lo, grid_cap=40)
+            assert relerr(out, ref) < tol, ('inner', shape)
+        if axis == 0 and len(shape) == 3:
+            # ranges of the last axis: rows = the middle axis, row pitch = the last extent
+            out = B.fftw.aligned(shape, dtype=dt, fill=0)
+            cuts = [0, 8, last - 3, last]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                plan.execute_chunk(device_ptr(a), device_ptr(out), 1.0, 1, lo, hi - lo, view_outer=shape[1],
+                                   view_ostride=last)
+            assert relerr(out, ref) < tol, ('last axis', shape)
+        plan.destroy()
+    # scatter form: FFT along axS of each rank's block, pieces stored into the owners' arrays
+    for shape, axS, axD, p, mode in (((8, 64, 48), 1, 0, 2, 1), ((8, 64, 48), 1, 2, 4, 2), ((6, 5, 128), 2, 1, 3, 2),
+                                     ((16, 1024, 24), 1, 0, 4, 1)):
+        g = rand(shape, dt, 9)
+        full = np.fft.fft(g.astype('D'), axis=axS)
+
+        def blocks(arr, ax):
+            out = []
+            for r in range(p):
+                n, s0 = _blockdist(shape[ax], p, r)
+                sl = [slice(None)] * len(shape)
+                sl[ax] = slice(s0, s0 + n)
+                out.append(np.ascontiguousarray(arr[tuple(sl)]))
+            return out
+        expect, src_np = blocks(full, axS), blocks(g, axD)
+        dst = [B.fftw.aligned(e.shape, dtype=dt, fill=0) for e in expect]
+        ptrs = [device_ptr(d) for d in dst]
+        for r in range(p):
+            class FakeComm(object):
+                ranks = tuple(range(p))
+                _r = r
+
+                def Get_size(self):
+                    return p
+
+                def Get_rank(self):
+                    return self._r
+            h = TransferHandle(FakeComm(), shape, dt.itemsize, src_np[r].shape, axS, expect[r].shape, axD, exchange=False)
+            plan = Plan(src_np[r].shape, src_np[r].shape, (axS,), [-1], prec)
+            a = B.fftw.aligned(src_np[r].shape, dtype=dt)
+            a[...] = src_np[r]
+            sshape = src_np[r].shape
+            extent = int(np.prod(sshape[axS + 1:])) if mode == 1 else int(np.prod(sshape[:axS]))
+            cuts = [0, extent // 2 + 1, extent]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                plan.execute_scatter_chunk(device_ptr(a), 1.0, h, 0, ptrs, 0, mode, lo, hi - lo)
+            plan.destroy()
+            h.destroy()
+        for r in range(p):
+            err = np.abs(np.asarray(dst[r]) - expect[r]).max() / np.abs(full).max()
+            assert err < tol, ('scatter', shape, axS, axD, p, mode, r, err)
+
+
 # ---------------------------------------------------------------------------
 # BASELINE config C2 at full size: properties that do not need a full oracle run
 # ---------------------------------------------------------------------------
