@@ -203,7 +203,8 @@ B2F_API int b2f_execute_chunk(b2f_plan plan, const void *d_in, void *d_out, doub
                       int grid_cap, void *stream);
 B2F_API int b2f_execute_scatter_chunk(b2f_plan plan, const void *d_in, double scale,
                       b2f_transfer t, int direction, void *const *peer_dst, int sync_flags,
-                      int mode, int64_t begin, int64_t count, int grid_cap, void *stream);
+                      int mode, int64_t begin, int64_t count, int64_t view_outer, int64_t view_ostride,
+                      int grid_cap, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,8 +52,8 @@ SYMBOLS = {
     'b2f_execute_chunk': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int64, C.c_int64,
                                     C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     'b2f_execute_scatter_chunk': (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
-                                            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
-                                            C.c_void_p]),
+                                            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                            C.c_int64, C.c_int, C.c_void_p]),
     'b2f_plan_can_scatter': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     'b2f_execute_scatter': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                       C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
@@ -163,11 +163,12 @@ class Plan(object):
                                       stream if stream is not None else current_stream_ptr()), 'b2f_execute_chunk')
 
     def execute_scatter_chunk(self, in_ptr, scale, transfer_handle, direction, peer_ptrs, sync_flags, mode, begin,
-                              count, grid_cap=0, stream=None):
+                              count, view_outer=0, view_ostride=0, grid_cap=0, stream=None):
         arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         check(lib().b2f_execute_scatter_chunk(self._h, C.c_void_p(in_ptr), float(scale), transfer_handle._h,
                                               int(direction), arr, int(sync_flags), int(mode), int(begin), int(count),
-                                              int(grid_cap), stream if stream is not None else current_stream_ptr()),
+                                              int(view_outer), int(view_ostride), int(grid_cap),
+                                              stream if stream is not None else current_stream_ptr()),
               'b2f_execute_scatter_chunk')
 
     def describe(self):

@@ -503,8 +503,13 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                     prm.inner = chunk->count;
                     prm.peer.ioff = chunk->begin;
                     if (chunk->view_outer > 0) {
+                        if (s.outer != 1) {
+                            set_error("a re-viewed partial launch needs the transformed axis to be the first one");
+                            return B2F_EUNSUPPORTED;
+                        }
                         outer = chunk->view_outer;
                         prm.in_ostride = prm.out_ostride = chunk->view_ostride;
+                        prm.peer.vstride = chunk->view_ostride;
                     }
                 }
                 prm.in = src = (const char*)src + off * esz;

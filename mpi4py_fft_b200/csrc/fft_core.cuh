@@ -245,11 +245,16 @@ struct PeerStore {
     long long stride;
     long long M, nD, ND, sD, Q;
     long long ooff, ioff;   // a launch over part of the block: its pencils start at (outer, inner) = (ooff, ioff)
+    long long vstride;      // > 0: the launch sees the block re-viewed as rows vstride apart: inner = o * vstride + i, outer = 0
     int p;            // owners of the transformed axis (0 = fused store not in use)
     int q, r;         // N = p*q + r: the first r owners hold q + 1 points
     int mode;
 
     B2F_HD void locate(long long o, long long i, long long* part, long long* rest) const {
+        if (vstride > 0) {
+            i += o * vstride;
+            o = 0;
+        }
         o += ooff;
         i += ioff;
         if (mode == 0) {

@@ -633,8 +633,8 @@ int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double sc
 
 int b2f_execute_scatter_chunk(b2f_plan plan, const void* d_in, double scale, b2f_transfer t, int direction,
                               void* const* peer_dst, int sync_flags, int mode, int64_t begin, int64_t count,
-                              int grid_cap, void* stream) {
-    ChunkSpec ch{mode, begin, count, 0, 0, grid_cap};
+                              int64_t view_outer, int64_t view_ostride, int grid_cap, void* stream) {
+    ChunkSpec ch{mode, begin, count, view_outer, view_ostride, grid_cap};
     return execute_scatter_impl(plan, d_in, nullptr, scale, t, direction, peer_dst, sync_flags, &ch, stream);
 }
 

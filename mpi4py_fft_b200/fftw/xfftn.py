@@ -139,6 +139,16 @@ class FFT(object):
         self.plan().execute_scatter(device_ptr(src), device_ptr(work) if work is not None else 0, scale,
                                     transfer_handle, direction, peer_ptrs, sync)
 
+    def execute_chunk(self, src, dst, scale, mode, begin, count, view_outer=0, view_ostride=0, grid_cap=0):
+        """part of a one-axis stage (b2f_execute_chunk)"""
+        self.plan().execute_chunk(device_ptr(src), device_ptr(dst), scale, mode, begin, count, view_outer,
+                                  view_ostride, grid_cap)
+
+    def execute_scatter_chunk(self, src, scale, transfer_handle, direction, peer_ptrs, sync_flags, mode, begin, count,
+                              view_outer=0, view_ostride=0, grid_cap=0):
+        self.plan().execute_scatter_chunk(device_ptr(src), scale, transfer_handle, direction, peer_ptrs, sync_flags,
+                                          mode, begin, count, view_outer, view_ostride, grid_cap)
+
     def __call__(self, input_array=None, output_array=None, implicit=True, normalize=False, **kw):
         """Compute the transform; returns the output array.
 

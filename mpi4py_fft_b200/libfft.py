@@ -102,6 +102,28 @@ class _Stage(object):
         self._planned.execute_scatter(src, work, self._owner.M if normalize else 1.0, transfer_handle,
                                       direction, peer_ptrs, getattr(peer_ptrs, 'sync', True))
 
+    # -- partial launches (pipelined redistribution, mpifft.Transform) ------------
+    @property
+    def chunkable(self):
+        """a one-axis complex Stockham stage can be launched in pieces"""
+        pl = self._planned
+        return (type(self) is _Stage and len(pl.axes) == 1 and pl.kind in (fftw.FFTW_FORWARD, fftw.FFTW_BACKWARD)
+                and pl.plan().describe().startswith('stockham'))
+
+    def scale_for(self, normalize):
+        if normalize is None:
+            normalize = self._default_normalize
+        return self._owner.M if normalize else 1.0
+
+    def run_chunk(self, src, dst, normalize, spec, grid_cap=0):
+        mode, begin, count, vo, vs = spec
+        self._planned.execute_chunk(src, dst, self.scale_for(normalize), mode, begin, count, vo, vs, grid_cap)
+
+    def run_scatter_chunk(self, src, normalize, transfer_handle, direction, peer_ptrs, sync_flags, spec, grid_cap=0):
+        mode, begin, count, vo, vs = spec
+        self._planned.execute_scatter_chunk(src, self.scale_for(normalize), transfer_handle, direction, peer_ptrs,
+                                            sync_flags, mode, begin, count, vo, vs, grid_cap)
+
     def __call__(self, input_array=None, output_array=None, **kw):
         normalize = kw.pop('normalize', self._default_normalize)
         src = self._planned._usable(input_array, self.input_shape, self.input_dtype)

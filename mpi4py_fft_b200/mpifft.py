@@ -158,6 +158,7 @@ class Transform(object):
         self._buffers = buffers
         self._ends = ends
         self._all_transfers = self._transfer   # PFFT replaces this with the forward-order list (collective order)
+        self._side = None                      # second stream of the pipelined redistribution
         self._plan = self._layout()
 
     # -- arrays -------------------------------------------------------------------
@@ -249,6 +250,77 @@ class Transform(object):
             self._plan[key] = ok
         return self._plan[key]
 
+    def _pipeline(self, i):
+        """Chunk plan for overlapping stage i (+ its redistribution) with stage i+1, or
+        None.  The producing stage stores chunk c into the peers' windows while the
+        consuming stage already transforms chunk c-1 on a second stream; chunks are
+        ranges of an array axis that neither stage transforms and the transfer does not
+        touch: the last axis (inner ranges, re-viewed rows where other axes lie
+        between) or the first one (outer ranges).  Geometry only: every rank of the
+        group takes the same decision."""
+        key = ('pipe', i)
+        if key in self._plan:
+            return self._plan[key]
+        plan = None
+        k = pipeline_chunks()
+        m = len(self._xfftn)
+        prod, cons = self._xfftn[i], self._xfftn[i + 1]
+        follows_trivially = (i + 2 >= m) or self._plan['trivial'][i + 1]
+        if k > 1 and follows_trivially and getattr(prod, 'chunkable', False) and getattr(cons, 'chunkable', False):
+            ps, cs = tuple(prod.output_shape), tuple(cons.input_shape)
+            nd = len(ps)
+            ap, ac = prod._planned.axes[0], cons._planned.axes[0]
+            pr = lambda t: int(np.prod(t)) if len(t) else 1
+            if nd >= 3 and ap != nd - 1 and ac != nd - 1 and ps[-1] == cs[-1] and ps[-1] >= k:
+                # ranges of the last axis
+                def view(shape, ax):
+                    mid = pr(shape[ax + 1:-1])
+                    if mid == 1:
+                        return (0, 0)                       # plain inner range
+                    if pr(shape[:ax]) != 1:
+                        return None                         # rows before AND between: not expressible
+                    return (mid, shape[-1])
+                vp, vc = view(ps, ap), view(cs, ac)
+                if vp is not None and vc is not None:
+                    # cut at multiples of 16 elements (tile rows stay aligned) when the axis is long enough
+                    g = 16 if ps[-1] >= 16 * k else 1
+                    cuts = sorted(set([0, ps[-1]] + [(ps[-1] // g * j // k) * g for j in range(1, k)]))
+                    plan = [((1, lo, hi - lo) + vp, (1, lo, hi - lo) + vc) for lo, hi in zip(cuts[:-1], cuts[1:])]
+            if plan is None and ap != 0 and ac != 0 and ps[0] == cs[0] and ps[0] >= k:
+                # ranges of the first axis = ranges of the outer index of both stages
+                rp, rc = pr(ps[1:ap]), pr(cs[1:ac])
+                cuts = [ps[0] * j // k for j in range(k + 1)]
+                plan = [((2, lo * rp, (hi - lo) * rp, 0, 0), (2, lo * rc, (hi - lo) * rc, 0, 0))
+                        for lo, hi in zip(cuts[:-1], cuts[1:])]
+        self._plan[key] = plan
+        return plan
+
+    def _run_pipelined(self, i, chunks, cur, recv, dst2, tr, direction, peers, normalize):
+        """stage i in chunks on the current stream (each followed by the group
+        barrier), stage i+1 chunk by chunk on a side stream"""
+        import torch
+        prod, cons = self._xfftn[i], self._xfftn[i + 1]
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        p = tr.comm.Get_size()
+        sms = pipeline_producer_sms(p)
+        handle = tr._plan()
+        for c, (pspec, cspec) in enumerate(chunks):
+            flags = (1 if c == 0 else 0) | 2          # enter once, leave after every chunk
+            prod.run_scatter_chunk(cur, normalize, handle, direction, peers, flags, pspec, grid_cap=sms)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                # the last chunk has the GPU to itself; the others share it with the producer
+                last = c + 1 == len(chunks)
+                cons.run_chunk(recv, dst2, normalize, cspec, grid_cap=0 if last else max(8, 148 - sms))
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+
     def _resolve(self, label, shape, dtype, src, out):
         if label == 'IN':
             return src
@@ -286,7 +358,12 @@ class Transform(object):
             self.input_array[...] = src
             src = self.input_array
         cur = src
+        skip = -1
         for i in range(m):
+            if i == skip:
+                # stage i already ran inside the pipelined redistribution before it; what follows
+                # it is a trivial transfer (an alias) or nothing
+                continue
             st = self._xfftn[i]
             dst = self._resolve(plan['b'][i], st.output_shape, st.output_dtype, src, out)
             if i + 1 < m and not plan['trivial'][i]:
@@ -297,6 +374,14 @@ class Transform(object):
                 label = plan['a'][i + 1]
                 direction = 0 if self._transfer[i].__name__ == 'forward' else 1
                 if table is not None and label in table:
+                    chunks = self._pipeline(i) if self._fused(i, st, tr, direction) else None
+                    if chunks:
+                        # stage i, the redistribution and stage i+1 overlapped chunk by chunk
+                        dst2 = self._resolve(plan['b'][i + 1], nxt.output_shape, nxt.output_dtype, src, out)
+                        self._run_pipelined(i, chunks, cur, recv, dst2, tr, direction, table[label], kw.get('normalize'))
+                        cur = dst2
+                        skip = i + 1
+                        continue
                     if self._fused(i, st, tr, direction):
                         # one launch: the stage's last pass stores into the owners' windows
                         st.run_scatter(cur, dst, kw.get('normalize'), tr._plan(), direction, table[label])
@@ -322,6 +407,27 @@ def p2p_enabled():
     unpack) are the default on a multi-GPU node; B2F_P2P=0 keeps the NCCL path."""
     import os
     return os.environ.get('B2F_P2P', '1') not in ('0', 'false', 'no', '')
+
+
+def pipeline_chunks():
+    """B2F_PIPELINE=K: chunks of the pipelined redistribution (0 or 1: off)"""
+    import os
+    try:
+        return int(os.environ.get('B2F_PIPELINE', '8'))
+    except ValueError:
+        return 0
+
+
+def pipeline_producer_sms(p):
+    """SMs given to the producing (NVLink-bound) stage of a pipelined redistribution
+    in a group of p ranks; the consuming stage gets the rest.  The remote share
+    (p-1)/p of the stage output crosses NVLink at about 1/8 of the HBM rate, so the
+    producer needs roughly 0.3 p/(p-1) of the GPU to keep the links busy."""
+    import os
+    env = os.environ.get('B2F_PIPE_SMS')
+    if env:
+        return int(env)
+    return int(min(120, max(32, round(148 * 0.30 * p / (p - 1)))))
 
 
 def fused_enabled():

@@ -11,20 +11,22 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('p2p', ['1', '0', 'put'])
+@pytest.mark.parametrize('p2p', ['1', 'nopipe', '0', 'put'])
 @pytest.mark.parametrize('world', [2, 4, 8])
 def test_pfft_over_nccl(world, p2p):
     """p2p=1 (default): stages store straight into the peers' CUDA-IPC windows
-    (fused) where they can, else the put kernel; p2p=put: stage, then put kernel;
+    (fused) where they can, pipelined with the consuming stage where the geometry
+    allows; nopipe: fused, one launch per stage; put: stage, then put kernel;
     p2p=0: pack -> NCCL send/recv -> unpack"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    port = 29500 + world + 20 * ['0', '1', 'put'].index(p2p)
+    port = 29500 + world + 20 * ['0', '1', 'put', 'nopipe'].index(p2p)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', str(port),
            os.path.join(ROOT, 'tests', 'mp_worker.py')]
-    env = dict(os.environ, B2F_P2P='0' if p2p == '0' else '1', B2F_FUSED='0' if p2p == 'put' else '1')
+    env = dict(os.environ, B2F_P2P='0' if p2p == '0' else '1', B2F_FUSED='0' if p2p == 'put' else '1',
+               B2F_PIPELINE='0' if p2p == 'nopipe' else '4')
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'MULTI_OK' in r.stdout, r.stdout[-6000:] + r.stderr[-3000:]
     if p2p != '0':

@@ -528,7 +528,7 @@ def test_partial_stage_launches(B, dtype):
         plan.destroy()
     # scatter form: FFT along axS of each rank's block, pieces stored into the owners' arrays
     for shape, axS, axD, p, mode in (((8, 64, 48), 1, 0, 2, 1), ((8, 64, 48), 1, 2, 4, 2), ((6, 5, 128), 2, 1, 3, 2),
-                                     ((16, 1024, 24), 1, 0, 4, 1)):
+                                     ((16, 1024, 24), 1, 0, 4, 1), ((64, 12, 40), 0, 1, 3, 3), ((512, 8, 24), 0, 1, 2, 3)):
         g = rand(shape, dt, 9)
         full = np.fft.fft(g.astype('D'), axis=axS)
 
@@ -558,10 +558,16 @@ def test_partial_stage_launches(B, dtype):
             a = B.fftw.aligned(src_np[r].shape, dtype=dt)
             a[...] = src_np[r]
             sshape = src_np[r].shape
-            extent = int(np.prod(sshape[axS + 1:])) if mode == 1 else int(np.prod(sshape[:axS]))
-            cuts = [0, extent // 2 + 1, extent]
-            for lo, hi in zip(cuts[:-1], cuts[1:]):
-                plan.execute_scatter_chunk(device_ptr(a), 1.0, h, 0, ptrs, 0, mode, lo, hi - lo)
+            if mode == 3:      # ranges of the last axis of a block whose FIRST axis is transformed (re-viewed rows)
+                cuts = [0, 7, sshape[-1]]
+                for lo, hi in zip(cuts[:-1], cuts[1:]):
+                    plan.execute_scatter_chunk(device_ptr(a), 1.0, h, 0, ptrs, 0, 1, lo, hi - lo,
+                                               view_outer=int(np.prod(sshape[1:-1])), view_ostride=sshape[-1])
+            else:
+                extent = int(np.prod(sshape[axS + 1:])) if mode == 1 else int(np.prod(sshape[:axS]))
+                cuts = [0, extent // 2 + 1, extent]
+                for lo, hi in zip(cuts[:-1], cuts[1:]):
+                    plan.execute_scatter_chunk(device_ptr(a), 1.0, h, 0, ptrs, 0, mode, lo, hi - lo)
             plan.destroy()
             h.destroy()
         for r in range(p):

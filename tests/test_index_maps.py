@@ -193,3 +193,38 @@ def test_distarray_metadata_needs_no_device():
         f = PFFT(COMM_WORLD, (16, 14, 12), dtype='d')
         assert f.global_shape(True) == (16, 14, 7)
         assert f.pencil[True].axis == 0 and f.pencil[False].axis == 2
+
+
+def test_pipeline_chunk_plans():
+    """which axis the pipelined redistribution cuts (Transform._pipeline): the last
+    axis where neither stage transforms it (inner ranges; re-viewed rows when other
+    axes lie between), else the first axis (outer ranges); r2c/c2r stages and
+    stages followed by another redistribution are not pipelined"""
+    os.environ['B2F_PIPELINE'] = '4'
+    try:
+        with virtual_world(2, 0):
+            odd = PFFT(COMM_WORLD, (64, 48, 96), dtype='D').forward._pipeline(1)
+            assert [c[0][1:3] for c in odd] == [(0, 16), (16, 32), (48, 16), (64, 32)]     # cuts at multiples of 16
+        with virtual_world(8, 3):
+            f = PFFT(COMM_WORLD, (1024, 1024, 1024), dtype='D')       # C3: grid [4, 2, 1]
+            assert [tuple(s.forward.input_shape) for s in f.xfftn] == [(256, 512, 1024), (256, 1024, 512), (1024, 256, 512)]
+            assert f.forward._pipeline(0) is None                     # stage 1 feeds another redistribution
+            fw = f.forward._pipeline(1)
+            # producer: inner ranges of axis 2; consumer: 256 rows 512 apart, ranges of the same axis
+            assert fw == [((1, 128 * j, 128, 0, 0), (1, 128 * j, 128, 256, 512)) for j in range(4)]
+            assert f.backward._pipeline(0) is None
+            bw = f.backward._pipeline(1)
+            # backward: the consumer transforms the last axis, so the first axis is cut (outer ranges)
+            assert bw == [((2, 64 * j, 64, 0, 0), (2, 64 * j * 512, 64 * 512, 0, 0)) for j in range(4)]
+        with virtual_world(2, 1):
+            f = PFFT(COMM_WORLD, (1024, 1024, 1024), dtype='D')       # slab [2, 1, 1]
+            fw = f.forward._pipeline(1)
+            assert fw == [((1, 256 * j, 256, 0, 0), (1, 256 * j, 256, 512, 1024)) for j in range(4)]
+            bw = f.backward._pipeline(0)
+            # producer transforms axis 0 of (1024, 512, 1024): re-viewed rows; consumer: plain inner ranges
+            assert bw == [((1, 256 * j, 256, 512, 1024), (1, 256 * j, 256, 0, 0)) for j in range(4)]
+            r = PFFT(COMM_WORLD, (64, 64, 64), dtype='d')
+            assert r.backward._pipeline(0) is not None                # c2c consumer
+            assert r.forward._pipeline(1) is not None
+    finally:
+        del os.environ['B2F_PIPELINE']
