@@ -262,9 +262,9 @@ class Transform(object):
         if key in self._plan:
             return self._plan[key]
         plan = None
-        k = pipeline_chunks()
         m = len(self._xfftn)
         prod, cons = self._xfftn[i], self._xfftn[i + 1]
+        k = pipeline_chunks(int(np.prod(prod.output_shape)) * np.dtype(prod.output_dtype).itemsize)
         follows_trivially = (i + 2 >= m) or self._plan['trivial'][i + 1]
         if k > 1 and follows_trivially and getattr(prod, 'chunkable', False) and getattr(cons, 'chunkable', False):
             ps, cs = tuple(prod.output_shape), tuple(cons.input_shape)
@@ -409,13 +409,21 @@ def p2p_enabled():
     return os.environ.get('B2F_P2P', '1') not in ('0', 'false', 'no', '')
 
 
-def pipeline_chunks():
-    """B2F_PIPELINE=K: chunks of the pipelined redistribution (0 or 1: off)"""
+def pipeline_chunks(block_bytes=None):
+    """Chunks of the pipelined redistribution.  B2F_PIPELINE=K forces K (0 or 1: off);
+    by default chunks of about 1 GiB (measured best on 2 and 4 B200s, profiles/
+    r1e_pipeline.txt: 8 GiB blocks K=8, 4 GiB blocks K=4) and no pipelining below
+    64 MiB, where the per-chunk group barrier costs more than the overlap gains."""
     import os
-    try:
-        return int(os.environ.get('B2F_PIPELINE', '8'))
-    except ValueError:
+    env = os.environ.get('B2F_PIPELINE')
+    if env is not None:
+        try:
+            return int(env)
+        except ValueError:
+            return 0
+    if block_bytes is None or block_bytes < (64 << 20):
         return 0
+    return int(max(2, min(16, block_bytes >> 30)))
 
 
 def pipeline_producer_sms(p):
