@@ -11,3 +11,4 @@ tail -1 gpurun_out/bench_ref.log
 tail -2 gpurun_out/bench_under_ncu.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fft_ -s 9 -c 3 -f -o gpurun_out/r1_full_1024 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
