@@ -297,9 +297,13 @@ def run_b200(args):
     # ---- end to end with host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
+        # every rank stages its own block through pinned host memory; whether the box has the
+        # room is decided collectively (a rank that bails out alone would strand the others)
+        h_in = h_out = None
+        why = ''
         try:
             import psutil
-            need = 2 * u.nbytes
+            need = 2 * u.nbytes * world          # all ranks share this host
             avail = psutil.virtual_memory().available
             if avail < need * 1.5:
                 raise MemoryError("host has %.0f GiB available, pinned staging needs %.0f GiB"
@@ -307,6 +311,15 @@ def run_b200(args):
             h_in = pinned_empty(u.shape, 'D')
             h_out = pinned_empty(u.shape, 'D')
             h_in[...] = 0.5
+        except Exception as exc:   # e.g. not enough host RAM for pinned staging buffers
+            why = repr(exc)[:200]
+            h_in = h_out = None
+        flag = torch.tensor([1.0 if h_in is not None else 0.0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) < 0.5:
+            e2e = {"value": None, "unit": "GPoints/s", "error": why or "another rank could not stage its block"}
+        else:
             e2e_steps = max(1, min(args.steps, 3))
 
             def e2e_step():
@@ -323,13 +336,26 @@ def run_b200(args):
             if world > 1:
                 dist.all_reduce(td, op=dist.ReduceOp.MAX)
             dt = float(td.item())
-            assert abs(h_out[0, 0, 0] - 0.5) < 1e-12
-            e2e = {"value": 2.0 * S ** 3 / dt / 1e9, "unit": "GPoints/s", "h2d_bytes_per_step": int(h_in.nbytes),
-                   "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                   "host_memory": "pinned"}
-            del h_in, h_out
-        except Exception as exc:   # e.g. not enough host RAM for pinned staging buffers
-            e2e = {"value": None, "unit": "GPoints/s", "error": repr(exc)[:200]}
+            good = abs(h_out[(0,) * h_out.ndim] - 0.5) < 1e-12
+            e2e = {"value": 2.0 * S ** 3 / dt / 1e9 if good else None, "unit": "GPoints/s",
+                   "h2d_bytes_per_step": int(h_in.nbytes) * world, "d2h_bytes_per_step": int(h_out.nbytes) * world,
+                   "ms_per_step": dt * 1e3, "steps": e2e_steps, "host_memory": "pinned, one block per rank"}
+            if not good:
+                e2e["error"] = "round trip through host buffers did not reproduce the input"
+        del h_in, h_out
+
+    # bytes every GPU pushes over NVLink per step (both directions of the transform): the share
+    # (p-1)/p of the block each redistribution moves; step time bounds the achieved rate from below
+    nvlink = None
+    if world > 1:
+        sent = 0
+        for t in fft.transfer:
+            p = t.comm.Get_size()
+            if p > 1:
+                sent += 2 * int(np.prod(t.subshapeA)) * t.dtype.itemsize * (p - 1) // p
+        nvlink = {"bytes_per_gpu_per_step": int(sent), "min_gbs_per_gpu": sent / (ms_per_step * 1e-3) / 1e9,
+                  "reference_gbs": 770.0, "note": "peer-copy reference of this pool (B200_PROFILING.md); "
+                  "redistributions are fused into the stages, so their NVLink time is not separable"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -359,7 +385,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (%.1f GiB per array per GPU)" % (u.nbytes / 2 ** 30),
                        "transfer": transfer_mode,
                        "roundtrip_max_err": err},
-            "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roofline, "nvlink": nvlink, "e2e": e2e, "cpu_baseline": cpu,
             "gpu_launches": int(launches),
         }
         print(json.dumps(line), flush=True)

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in default 100 102; do
-if [ $v = default ]; then unset B2F_VARIANT_TMA; else export B2F_VARIANT_TMA=$v; fi
-( timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu ) > gpurun_out/bench_var_$v.log 2>&1
-echo "variant_tma=$v $(tail -1 gpurun_out/bench_var_$v.log | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(round(d["value"],2), [round(s["ms"],2) for s in d["roofline"]["per_stage"]], d["clocks"]["sm_mhz"])')"
-done
+( timeout 200 python tools/sweep.py --size 1024 --reps 5 --axes 1 --engine tma --variants 100,102 ) > gpurun_out/diag_a.log 2>&1
+( timeout 200 python tools/sweep.py --size 1024 --reps 5 --axes 1 --engine tma --variants 100,102 --prealloc-gib 48 ) > gpurun_out/diag_b.log 2>&1
+( timeout 200 python tools/sweep.py --size 1024 --reps 40 --axes 1 --engine tma --variants 100,102 ) > gpurun_out/diag_c.log 2>&1
+grep "axis" gpurun_out/diag_a.log gpurun_out/diag_b.log gpurun_out/diag_c.log

@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--axes', default='2,1,0')
     ap.add_argument('--inplace', action='store_true')
+    ap.add_argument('--prealloc-gib', type=int, default=0, help='allocate (and touch) this much memory first')
     ap.add_argument('--engine', default='reg', choices=['reg', 'tma'], help='strided axes: register path or TMA-staged')
     args = ap.parse_args()
     import torch
@@ -42,6 +43,7 @@ def main():
             variants += list(range(int(lo), int(hi) + 1))
         else:
             variants.append(int(part))
+    ballast = [torch.zeros(1 << 30, dtype=torch.uint8, device='cuda') for _ in range(args.prealloc_gib)]
     a = B.fftw.aligned(shape, dtype=args.dtype)
     b = B.fftw.aligned(shape, dtype=args.dtype)
     a.tensor.copy_(torch.view_as_complex(torch.rand(shape + (2,), dtype=a.tensor.real.dtype, device='cuda')))
