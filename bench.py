@@ -239,18 +239,27 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
+    # per-direction marks inside the same timed region (t_fwd, t_bwd)
+    mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev[0].record(stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        uh = fft.forward(u)
+        mid[k].record(stream)
+        fft.backward(uh, back)
+        end[k].record(stream)
     ev[1].record(stream)
     barrier()
     t_ms = ev[0].elapsed_time(ev[1])
     launches = _lib.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
-    tt = torch.tensor([t_ms], dtype=torch.float64, device='cuda')
+    starts = [ev[0]] + end[:-1]
+    fwd = float(np.median([a.elapsed_time(b) for a, b in zip(starts, mid)]))
+    bwd = float(np.median([a.elapsed_time(b) for a, b in zip(mid, end)]))
+    tt = torch.tensor([t_ms, fwd, bwd], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = float(tt.item())
+    t_ms, fwd, bwd = (float(x) for x in tt.tolist())
     ms_per_step = t_ms / args.steps
     value = 2.0 * S ** 3 / (ms_per_step * 1e-3) / 1e9
 
@@ -384,6 +393,8 @@ def run_b200(args):
             "config": {"workload": workload_name(S), "grid": grid, "local_shape": list(u.shape),
                        "l2": "inputs larger than L2 (%.1f GiB per array per GPU)" % (u.nbytes / 2 ** 30),
                        "transfer": transfer_mode,
+                       "forward_ms_median": fwd, "backward_ms_median": bwd,
+                       "forward_gpoints_s": S ** 3 / (fwd * 1e-3) / 1e9, "backward_gpoints_s": S ** 3 / (bwd * 1e-3) / 1e9,
                        "roundtrip_max_err": err},
             "clocks": clk, "roofline": roofline, "nvlink": nvlink, "e2e": e2e, "cpu_baseline": cpu,
             "gpu_launches": int(launches),
