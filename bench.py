@@ -380,6 +380,10 @@ def run_b200(args):
     p2p_name = ('stage kernels store into peer windows (fused, CUDA IPC over NVLink)' if fused and all(fused) else
                 'fused where possible, else put kernel over CUDA-IPC windows' if any(fused) else
                 'put kernel over CUDA-IPC windows')
+    piped = [v for k, v in list(fft.forward._plan.items()) + list(fft.backward._plan.items())
+             if isinstance(k, tuple) and k[0] == 'pipe' and v]
+    if piped:
+        p2p_name += '; last redistribution of each direction pipelined with its consumer in %d chunks' % len(piped[0])
     modes = sorted(set(p2p_name if v is not None else 'pack + NCCL send/recv + unpack'
                        for v in fft._buffers.peers.values()))
     transfer_mode = ' / '.join(modes) if modes else ('none (single rank)' if world == 1 else 'pack + NCCL send/recv + unpack')

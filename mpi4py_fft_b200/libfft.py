@@ -107,8 +107,12 @@ class _Stage(object):
     def chunkable(self):
         """a one-axis complex Stockham stage can be launched in pieces"""
         pl = self._planned
-        return (type(self) is _Stage and len(pl.axes) == 1 and pl.kind in (fftw.FFTW_FORWARD, fftw.FFTW_BACKWARD)
-                and pl.plan().describe().startswith('stockham'))
+        if type(self) is not _Stage or len(pl.axes) != 1 or pl.kind not in (fftw.FFTW_FORWARD, fftw.FFTW_BACKWARD):
+            return False
+        try:
+            return pl.plan().describe().startswith('stockham')
+        except Exception:       # e.g. tables of a chirp-z stage cannot be built (no device): not chunkable
+            return False
 
     def scale_for(self, normalize):
         if normalize is None:
