@@ -228,3 +228,44 @@ def test_pipeline_chunk_plans():
             assert r.forward._pipeline(1) is not None
     finally:
         del os.environ['B2F_PIPELINE']
+
+
+@pytest.mark.parametrize('nranks', [1, 2, 3, 4])
+def test_padded_plan_matrix_vs_oracle(nranks):
+    """the padded half of the reference's PFFT test matrix (tests/test_mpifft.py:179-236:
+    shapes from (12, 13), padding 1.5 on every axis, the listed axes variants, slab
+    and pencil grids): physical / spectral global shapes, every rank's local slices
+    and the per-stage shapes of the product equal the oracle's restatement of
+    mpifft.py:247-253 + libfft.py:424-434 (itself pinned against fixtures of the
+    unmodified reference)"""
+    from itertools import product
+    import pfft_oracle as O
+    sizes = (12, 13)
+    checked = 0
+    for dim, allaxes, grids in ((2, [None, (-1,), (-2,), (-1, -2), (-2, -1), (-1, 0), (0, -1), ((0,), (1,))], (None,)),
+                                (3, [None, ((0,), (1,), (2,)), ((0,), (-2,), (-1,))], ((-1,), None))):
+        for shape in product(*([sizes] * dim)):
+            for dtype in 'dD':
+                for grid in grids:
+                    for axes in allaxes:
+                        kw = dict(shape=shape, axes=axes, dtype=dtype, padding=[1.5] * dim, grid=grid)
+                        try:
+                            orc = O.OraclePFFT(nranks, shape, axes=axes, dtype=dtype, grid=grid, padding=[1.5] * dim)
+                        except AssertionError:
+                            continue        # more ranks than a distributed extent can hold (the reference skips these too)
+                        lay = orc.layout()
+                        for r in range(nranks):
+                            with virtual_world(nranks, r):
+                                fft = PFFT(COMM_WORLD, **{k: v for k, v in kw.items() if v is not None})
+                                assert list(fft.global_shape(False)) == lay['input_shape'], kw
+                                assert list(fft.global_shape(True)) == lay['output_shape'], kw
+                                assert fft.dtype(True).char == lay['output_dtype']
+                                assert fft.local_slice(False) == orc.local_slice(r, False), kw
+                                assert fft.local_slice(True) == orc.local_slice(r, True), kw
+                                for st, ost in zip(fft.xfftn, lay['ranks'][r]['stages']):
+                                    assert list(st.axes) == ost['axes']
+                                    assert list(st.forward.input_shape) == ost['in_subshape'], kw
+                                    assert list(st.forward.output_shape) == ost['out_subshape'], kw
+                                assert len(fft.axes) == len(fft.xfftn) == len(fft.transfer) + 1
+                        checked += 1
+    assert checked >= 40
