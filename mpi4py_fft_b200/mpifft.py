@@ -101,9 +101,10 @@ class _Buffers(object):
         """``groups``: the transfer communicators -- when given (PFFT.destroy is
         collective, as the reference's) every rank unmaps its peers' windows before
         any rank releases its own."""
-        if self.windows:
+        if self.windows is not None:      # set up (or attempted) on every rank alike: the barriers below must match
             import torch
-            torch.cuda.synchronize()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
             for comm in groups:               # nobody is still storing into a window
                 if comm.Get_size() > 1:
                     comm.Barrier()

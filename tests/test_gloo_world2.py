@@ -122,3 +122,86 @@ def test_transfer_exchange_over_gloo(world, shape, dtype):
         p.join(60)
     for rank, msg in results:
         assert msg == 'ok', "rank %d:\n%s" % (rank, msg)
+
+
+# ---------------------------------------------------------------------------
+# negotiation of the peer-memory windows (mpifft._Buffers.setup_windows): the
+# host-side protocol on two CPU processes with a stand-in for the CUDA-IPC window
+# ---------------------------------------------------------------------------
+def _window_worker(rank, world, port, fail_rank, q):
+    try:
+        sys.path.insert(0, ROOT)
+        os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        from mpi4py_fft_b200 import PFFT, COMM_WORLD, _lib
+
+        class FakeWindow(object):
+            """stands in for _lib.Window: no device memory, handles are plain bytes"""
+            made = []
+
+            def __init__(self, nbytes):
+                if rank == fail_rank:
+                    raise RuntimeError("cudaIpcGetMemHandle: not permitted (simulated)")
+                self.nbytes = int(nbytes)
+                self.ptr = 0x1000 * (rank + 1) + len(FakeWindow.made)
+                self.opened = []
+                FakeWindow.made.append(self)
+
+            def handle(self):
+                return ('rank%d:%d' % (rank, self.ptr)).encode().ljust(64, b'.')
+
+            def open_peer(self, h):
+                assert len(h) == 64 and not h.startswith(('rank%d:' % rank).encode())
+                self.opened.append(h)
+                return 0x900000 + int(h.split(b':')[1].rstrip(b'.'))
+
+            def close_peers(self):
+                self.opened = []
+
+            def free(self):
+                self.ptr = 0
+
+        _lib.Window = FakeWindow
+        fft = PFFT(COMM_WORLD, (8, 6, 4), dtype='D')
+        assert fft.forward._plan['windowed'] and fft.forward._plan['a'][-1].startswith('W')
+        buf = fft._buffers
+        buf.setup_windows(fft.transfer)
+        nontrivial = [t for t in fft.transfer if t.comm.Get_size() > 1]
+        assert len(nontrivial) == 1
+        table = buf.peers[id(nontrivial[0])]
+        if fail_rank is None:
+            # both ranks mapped each other's windows: per label one pointer per group rank, own one in place
+            assert set(table) == set(buf.need)
+            for label, ptrs in table.items():
+                assert len(ptrs) == world and ptrs[rank] == buf.windows[label].ptr
+                assert all(p >= 0x900000 for j, p in enumerate(ptrs) if j != rank)
+        else:
+            # one rank could not export: BOTH fall back to the NCCL path for this group, nobody hangs
+            assert table is None
+        buf.free([t.comm for t in fft.transfer])
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, 'ok'))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.parametrize('fail_rank', [None, 1, 0])
+def test_window_negotiation_over_gloo(fail_rank):
+    """the windows protocol is collective and all-or-nothing per group: handles are
+    exchanged through the host, every rank maps its peers, and a rank that cannot
+    export (IPC not permitted in its container) makes the whole group keep the NCCL
+    exchange instead of deadlocking or diverging"""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_window_worker, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    for rank, msg in results:
+        assert msg == 'ok', "rank %d:\n%s" % (rank, msg)
