@@ -114,6 +114,22 @@ def cpu_reference(size, steps, warmup, max_ranks=8):
                               sample="%d^3 complex128 fwd+bwd, %d steps; %s" % (size, steps, what))
 
 
+def cpu_best_library(size, steps=3):
+    """The strongest CPU library line of the box for context: pocketfft's
+    threaded fftn / ifftn on the undistributed array, every host core (not the reference's path)."""
+    import scipy.fft as sfft
+    cores = len(os.sched_getaffinity(0))
+    x = np.random.default_rng(0).random((size,) * 3) + 0j
+    sfft.ifftn(sfft.fftn(x, workers=cores), workers=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = sfft.fftn(x, workers=cores)
+        sfft.ifftn(y, workers=cores)
+    t = (time.perf_counter() - t0) / steps
+    return {"value": 2.0 * size ** 3 / t / 1e9, "unit": "GPoints/s", "cores": cores,
+            "what": "scipy.fft.fftn + ifftn(workers=%d) on %d^3 complex128, undistributed" % (cores, size)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -374,6 +390,10 @@ def run_b200(args):
                    "sample": info['sample'], "ms_per_step": ms, "host_cores": info['host_cores']}
         except Exception as exc:
             cpu = {"value": None, "unit": "GPoints/s", "error": repr(exc)[:200]}
+        try:
+            cpu["best_library"] = cpu_best_library(args.cpu_size)
+        except Exception as exc:
+            cpu["best_library"] = {"value": None, "error": repr(exc)[:200]}
 
     fused = [v for k, v in list(fft.forward._plan.items()) + list(fft.backward._plan.items())
              if isinstance(k, tuple) and k[0] == 'fused']
