@@ -57,7 +57,7 @@ def workload_name(size):
 # ---------------------------------------------------------------------------
 # CPU arm: the reference's PFFT on host cores
 # ---------------------------------------------------------------------------
-def cpu_reference(size, steps, warmup, max_ranks=8):
+def cpu_reference(size, steps, warmup, max_ranks=16):
     """Times the reference's own forward+backward on the host.  Returns
     (gpoints_per_s, ms_per_step, info dict)."""
     cores = len(os.sched_getaffinity(0))
