@@ -126,63 +126,75 @@
 //   MINB    min CTAs per SM  +  16 * OPT   (OPT bit 0: pass twiddles live in shared
 //           memory; bit 1: cp.async requests of the next tile are spread over the
 //           current tile's phases; bit 2: L2 prefetch of the tile after next) -- fft_tma.cuh
-#define B2F_TMA_TABLE(X)                           \
-    X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8)             \
-    X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8)            \
-    X(128, 0, 16, 16, 30, 2, 0, 1, 16, 8)          \
-    X(128, 1, 16, 8, 30, 2, 0, 1, 16, 8)           \
-    X(128, 2, 16, 16, 30, 2, 0, 17, 16, 8)         \
-    X(128, 3, 16, 8, 30, 2, 0, 17, 16, 8)          \
-    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)          \
-    X(256, 1, 16, 16, 30, 2, 0, 1, 16, 16)         \
-    X(256, 2, 16, 8, 30, 2, 0, 17, 16, 16)         \
-    X(256, 3, 16, 16, 30, 2, 0, 17, 16, 16)        \
-    X(512, 0, 16, 8, 3, 1, 1, 2, 8, 8, 8)          \
-    X(512, 1, 32, 8, 5, 1, 1, 1, 32, 16)           \
-    X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8)         \
-    X(512, 3, 16, 4, 3, 2, 0, 1, 8, 8, 8)          \
-    X(512, 4, 8, 8, 3, 1, 1, 1, 8, 8, 8)           \
-    X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16)          \
-    X(512, 6, 32, 16, 5, 1, 1, 1, 32, 16)          \
-    X(512, 7, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
-    X(512, 8, 16, 8, 30, 2, 0, 17, 8, 8, 8)        \
-    X(512, 9, 32, 16, 5, 1, 1, 17, 32, 16)         \
-    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
-    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
-    X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8)        \
-    X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32)          \
-    X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8)        \
-    X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32)          \
-    X(1024, 6, 32, 8, 5, 1, 1, 17, 32, 32)         \
+#define B2F_TMA_TABLE_A(X) \
+    X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8) \
+    X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8) \
+    X(128, 0, 16, 16, 30, 2, 0, 1, 16, 8) \
+    X(128, 1, 16, 8, 30, 2, 0, 1, 16, 8) \
+    X(128, 2, 16, 16, 30, 2, 0, 17, 16, 8) \
+    X(128, 3, 16, 8, 30, 2, 0, 17, 16, 8) \
+    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16) \
+    X(256, 1, 16, 16, 30, 2, 0, 1, 16, 16) \
+    X(256, 2, 16, 8, 30, 2, 0, 17, 16, 16) \
+    X(256, 3, 16, 16, 30, 2, 0, 17, 16, 16)
+
+#define B2F_TMA_TABLE_B(X) \
+    X(512, 0, 16, 8, 3, 1, 1, 2, 8, 8, 8) \
+    X(512, 1, 32, 8, 5, 1, 1, 1, 32, 16) \
+    X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8) \
+    X(512, 3, 16, 4, 3, 2, 0, 1, 8, 8, 8) \
+    X(512, 4, 8, 8, 3, 1, 1, 1, 8, 8, 8) \
+    X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16) \
+    X(512, 6, 32, 16, 5, 1, 1, 1, 32, 16) \
+    X(512, 7, 16, 16, 3, 1, 1, 1, 8, 8, 8) \
+    X(512, 8, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
+    X(512, 9, 32, 16, 5, 1, 1, 17, 32, 16)
+
+#define B2F_TMA_TABLE_C(X) \
+    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32) \
+    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8) \
+    X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8) \
+    X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32) \
+    X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8) \
+    X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32) \
+    X(1024, 6, 32, 8, 5, 1, 1, 17, 32, 32) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
+#define B2F_TMA_TABLE(X) B2F_TMA_TABLE_A(X) B2F_TMA_TABLE_B(X) B2F_TMA_TABLE_C(X)
+
 // the same pipeline filled by cp.async instead of TMA (variant_tma = 100 + VAR)
-#define B2F_CPA_TABLE(X)                           \
-    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)          \
-    X(512, 0, 16, 8, 30, 2, 0, 1, 8, 8, 8)         \
-    X(512, 1, 32, 16, 5, 1, 1, 1, 32, 16)          \
-    X(512, 2, 16, 16, 3, 1, 1, 1, 8, 8, 8)         \
-    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32)          \
-    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8)        \
-    X(1024, 2, 32, 8, 5, 1, 1, 17, 32, 32)         \
-    X(1024, 3, 32, 8, 5, 1, 1, 33, 32, 32)         \
-    X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32)         \
-    X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8)       \
-    X(512, 3, 32, 16, 5, 1, 1, 49, 32, 16)         \
-    X(512, 4, 16, 8, 30, 2, 0, 49, 8, 8, 8)        \
-    X(512, 5, 32, 16, 5, 1, 1, 17, 32, 16)         \
-    X(512, 6, 16, 8, 30, 2, 0, 17, 8, 8, 8)        \
-    X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16)         \
-    X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16)        \
-    X(256, 3, 16, 16, 30, 2, 0, 81, 16, 16)        \
-    X(192, 0, 24, 16, 30, 2, 0, 17, 24, 8)         \
-    X(384, 0, 24, 8, 30, 2, 0, 17, 6, 8, 8)        \
-    X(384, 1, 24, 16, 30, 1, 0, 17, 6, 8, 8)       \
-    X(768, 0, 24, 8, 30, 1, 0, 17, 12, 8, 8)       \
-    X(768, 1, 24, 8, 3, 1, 1, 17, 12, 8, 8)        \
-    X(512, 7, 32, 16, 5, 1, 1, 81, 32, 16)         \
-    X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32)         \
+#define B2F_CPA_TABLE_A(X) \
+    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16) \
+    X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16) \
+    X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16) \
+    X(256, 3, 16, 16, 30, 2, 0, 81, 16, 16) \
+    X(192, 0, 24, 16, 30, 2, 0, 17, 24, 8) \
+    X(384, 0, 24, 8, 30, 2, 0, 17, 6, 8, 8) \
+    X(384, 1, 24, 16, 30, 1, 0, 17, 6, 8, 8)
+
+#define B2F_CPA_TABLE_B(X) \
+    X(512, 0, 16, 8, 30, 2, 0, 1, 8, 8, 8) \
+    X(512, 1, 32, 16, 5, 1, 1, 1, 32, 16) \
+    X(512, 2, 16, 16, 3, 1, 1, 1, 8, 8, 8) \
+    X(512, 3, 32, 16, 5, 1, 1, 49, 32, 16) \
+    X(512, 4, 16, 8, 30, 2, 0, 49, 8, 8, 8) \
+    X(512, 5, 32, 16, 5, 1, 1, 17, 32, 16) \
+    X(512, 6, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
+    X(768, 0, 24, 8, 30, 1, 0, 17, 12, 8, 8) \
+    X(768, 1, 24, 8, 3, 1, 1, 17, 12, 8, 8) \
+    X(512, 7, 32, 16, 5, 1, 1, 81, 32, 16)
+
+#define B2F_CPA_TABLE_C(X) \
+    X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32) \
+    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8) \
+    X(1024, 2, 32, 8, 5, 1, 1, 17, 32, 32) \
+    X(1024, 3, 32, 8, 5, 1, 1, 33, 32, 32) \
+    X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32) \
+    X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8) \
+    X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
+
+#define B2F_CPA_TABLE(X) B2F_CPA_TABLE_A(X) B2F_CPA_TABLE_B(X) B2F_CPA_TABLE_C(X)
 
 // real transforms (r2c / c2r of even length 2N through the N-point schedule,
 // fft_pow2.cuh fft_real_kernel):  X(N, E, P, PS, MINB, radices...), one row per N
