@@ -16,13 +16,13 @@ pytestmark = pytest.mark.gpu
 
 def test_taylor_green_energy():
     sys.path.insert(0, os.path.join(ROOT, 'examples'))
-    import spectral_dns_solver as dns
+    import taylor_green_dns as dns
     k = dns.solve(6)
     assert round(k - 0.124953117517, 7) == 0, k
 
 
 def test_taylor_green_energy_dealiased():
     sys.path.insert(0, os.path.join(ROOT, 'examples'))
-    import spectral_dns_solver as dns
-    k = dns.solve(6, padding=True)
+    import taylor_green_dns as dns
+    k = dns.solve(6, dealias=True)
     assert round(k - 0.124953117517, 7) == 0, k
