@@ -88,6 +88,13 @@ class _Buffers(object):
             # the decision must be the same on every rank of the group
             agreed = all(comm.allgather(table is not None))
             self.peers[id(t)] = table if agreed else None
+            if not agreed and me == 0:
+                import warnings
+                reasons = [e[1].get('error') for e in everyone if isinstance(e[1], dict) and e[1].get('error')]
+                warnings.warn("mpi4py_fft_b200: peer-memory windows are not available in this group (%s); "
+                              "its redistributions use pack + NCCL + unpack" % (reasons[0] if reasons else
+                                                                                "a peer window could not be mapped"),
+                              RuntimeWarning)
 
     def window_view(self, label, shape, dtype):
         import torch
