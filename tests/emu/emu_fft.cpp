@@ -623,3 +623,58 @@ extern "C" int emu_chirpz(int precision, int kind, long long n, long long outer,
     if (precision == 8) return emu_chirp_dispatch<double>(sp.M, strided, prm, outer);
     return emu_chirp_dispatch<float>(sp.M, strided, prm, outer);
 }
+
+// ---- partial launches of a fused stage (capi.cu run_plan + ChunkSpec restated for
+// the test): the same pointer shifts / extents / PeerStore offsets the library
+// applies, then the kernels' own per-thread code.  mode 1 = inner range (with
+// view_outer > 0: rows view_ostride apart, transformed axis first), 2 = outer range.
+extern "C" int emu_fft_scatter_chunk(int precision, int ndims, const long long* shape, int axisS, int axisD, int p,
+                                     int rank, const void* in, void* const* peer_dst, double scale, int swap,
+                                     int mode, long long begin, long long count, long long view_outer,
+                                     long long view_ostride) {
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    if (peer_store_build(&prm.peer, ndims, shape, axisS, axisD, p, rank, peer_dst)) return -2;
+    long long nD, sD;
+    put_blockdist(shape[axisD], p, rank, &nD, &sD);
+    long long outer = 1, inner = 1;
+    for (int i = 0; i < axisS; ++i) outer *= (i == axisD ? nD : shape[i]);
+    for (int i = axisS + 1; i < ndims; ++i) inner *= (i == axisD ? nD : shape[i]);
+    const int n = (int)shape[axisS];
+    const bool strided = inner > 1;
+    prm.scale = scale;
+    prm.swap = swap;
+    if (strided) {
+        prm.in_ostride = prm.out_ostride = (long long)n * inner;
+        prm.in_nstride = prm.out_nstride = inner;
+        prm.inner = inner;
+    } else {
+        prm.in_ostride = prm.out_ostride = n;
+        prm.npencils = outer;
+    }
+    const long long esz = 2LL * precision;
+    long long off;
+    if (mode == 2) {
+        if (begin + count > outer || view_outer) return -4;
+        off = begin * prm.in_ostride;
+        outer = count;
+        prm.npencils = outer;
+        prm.peer.ooff = begin;
+    } else {
+        if (!strided || begin + count > inner) return -4;
+        off = begin;
+        prm.inner = count;
+        prm.peer.ioff = begin;
+        if (view_outer > 0) {
+            if (outer != 1) return -4;
+            outer = view_outer;
+            prm.in_ostride = prm.out_ostride = view_ostride;
+            prm.peer.vstride = view_ostride;
+        }
+    }
+    prm.in = (const char*)in + off * esz;
+    prm.out = nullptr;
+    if (outer == 0 || (strided && prm.inner == 0)) return 0;
+    if (precision == 8) return emu_dispatch<double>(n, 0, strided, prm, outer);
+    return emu_dispatch<float>(n, 0, strided, prm, outer);
+}

@@ -61,3 +61,49 @@ def test_fused_stage_and_transfer(emu, case, prec):
         for r in range(p):
             err = np.abs(dst[r] - expect[r]).max() / np.abs(full).max()
             assert err < tol, (case, prec, swap, r, err)
+
+
+# group-local shape, axisS, axisD, ranks, how the stage is cut: 'inner', 'outer' or 'rows'
+# ('rows' = ranges of the last axis of a block whose FIRST axis is transformed, re-viewed)
+CHUNKED = [
+    ((6, 64, 40), 1, 0, 2, 'inner'),
+    ((6, 64, 40), 1, 2, 3, 'outer'),
+    ((8, 5, 128), 2, 1, 2, 'outer'),
+    ((64, 12, 40), 0, 1, 3, 'rows'),
+    ((64, 12, 40), 0, 2, 2, 'rows'),
+    ((4, 1024, 24), 1, 0, 4, 'inner'),
+]
+
+
+@pytest.mark.parametrize('case', CHUNKED)
+def test_fused_stage_in_pieces(emu, case):
+    """the pipelined redistribution's producer: the fused stage launched in pieces
+    (PeerStore ooff / ioff / vstride, shifted base pointers) stores exactly what
+    the whole launch stores -- the library's parameter edits restated in the
+    emulator entry point, the kernels' own per-thread code underneath"""
+    shape, axS, axD, p, how = case
+    rng = np.random.default_rng(3)
+    g = rng.random(shape) + 1j * rng.random(shape)
+    n = shape[axS]
+    shp = (ctypes.c_longlong * len(shape))(*shape)
+    full = np.fft.fft(g, axis=axS)
+    expect = split_blocks(full, axS, p)
+    src = split_blocks(g, axD, p)
+    dst = [np.full(e.shape, np.nan, dtype=complex) for e in expect]
+    ptrs = (ctypes.c_void_p * p)(*[d.ctypes.data for d in dst])
+    for r in range(p):
+        ss = src[r].shape
+        if how == 'outer':
+            extent, mode, view = int(np.prod(ss[:axS])), 2, (0, 0)
+        elif how == 'inner':
+            extent, mode, view = int(np.prod(ss[axS + 1:])), 1, (0, 0)
+        else:
+            extent, mode, view = ss[-1], 1, (int(np.prod(ss[1:-1])), ss[-1])
+        cuts = sorted(set([0, extent // 3, extent // 3 + 1, extent]))
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            rc = emu.emu_fft_scatter_chunk(8, len(shape), shp, axS, axD, p, r, src[r].ctypes.data, ptrs, 1.0, 0,
+                                           mode, lo, hi - lo, view[0], view[1])
+            assert rc == 0, (case, r, lo, hi, rc)
+    for r in range(p):
+        err = np.abs(dst[r] - expect[r]).max() / np.abs(full).max()
+        assert err < 2e-15, (case, r, err)
