@@ -25,6 +25,7 @@
 #include "internal.h"
 #include "fft_configs.h"
 #include "chirpz_host.h"
+#include "rot_plan.h"
 
 #define B2F_GENERIC_MAX_N 4096
 
@@ -242,6 +243,11 @@ struct b2f_plan_s {
     int kind0;
     std::vector<long long> sizes_in, sizes_out;
     std::vector<Step> steps;
+    // alternative schedule for out-of-place execution (empty: none)
+    std::vector<RotPlanStep> rot;
+    bool rot_swap = false;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long long>& shp_in,
@@ -373,6 +379,12 @@ int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int6
         // splits -- and only the last step can store into the peers' windows
         for (int i = 0; i < naxes && rc == B2F_OK; ++i)
             rc = add_step(pl, k0, ax[i], pl->sizes_in, pl->sizes_out, 2, 2, i == 0 ? BUF_IN : BUF_OUT, BUF_OUT);
+        if (rc == B2F_OK && option("rotate", 1)) {
+            long long elems = 0;
+            if (build_rotation(ndims, pl->sizes_in.data(), ax.data(), naxes, &pl->rot, &elems))
+                pl->scratch_bytes = (size_t)elems * 2 * precision;
+            pl->rot_swap = (k0 == B2F_BACKWARD);
+        }
     } else if (k0 == B2F_R2C) {
         if (!same_except(last) || sizes_out[last] != sizes_in[last] / 2 + 1) rc = B2F_EINVAL;
         if (rc == B2F_OK) rc = add_step(pl, B2F_R2C, last, pl->sizes_in, pl->sizes_out, 1, 2, BUF_IN, BUF_OUT);
@@ -450,6 +462,40 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
         if (!ok) {
             set_error("partial execution needs a one-axis Stockham stage and a range inside the block");
             return B2F_EUNSUPPORTED;
+        }
+    }
+    if (!pl->rot.empty() && !peer_last && !before_last && !(chunk && chunk->mode != 0) && option("rotate", 1)) {
+        // out of place and not overlapping: the first step writes d_out while d_in is still being read
+        const char* a = (const char*)d_in;
+        const char* b = (const char*)d_out;
+        const bool apart = (a + pl->scratch_bytes <= b) || (b + pl->scratch_bytes <= a);
+        if (apart) {
+            if (!pl->scratch) {
+                cudaError_t e = cudaMalloc(&pl->scratch, pl->scratch_bytes);
+                if (e != cudaSuccess) {
+                    pl->scratch = nullptr;
+                    (void)cudaGetLastError();
+                }
+            }
+            if (pl->scratch) {
+                const int vr = (int)option("variant_rot", -1);
+                // bulk copies need 16-byte aligned pencils (checked before the first launch: the
+                // schedule cannot be abandoned half way)
+                const bool ok = !(((uintptr_t)d_in | (uintptr_t)d_out) & 15);
+                const int mask = (int)option("rot_step_mask", 7);   // profiling: run a subset of the steps
+                for (size_t si = 0; si < pl->rot.size() && ok; ++si) {
+                    const RotPlanStep& r = pl->rot[si];
+                    if (!((mask >> si) & 1)) continue;
+                    void* bufs[3] = {const_cast<void*>(d_in), d_out, pl->scratch};
+                    RotStep rs{bufs[r.src], bufs[r.dst], r.batches, r.I, r.O, r.in_i, r.in_o, r.in_b,
+                               r.out_o, r.out_n, r.out_b, si + 1 == pl->rot.size() ? scale : 1.0,
+                               pl->rot_swap ? 1 : 0, 0};
+                    cudaError_t e = launch_rot(pl->precision, r.n, vr >= 0 ? vr : rot_default(r.n), rs, st);
+                    if (e == cudaErrorInvalidValue && vr >= 0) e = launch_rot(pl->precision, r.n, rot_default(r.n), rs, st);
+                    if (e != cudaSuccess) return cuda_fail(e, "b2f_execute: rotating kernel launch");
+                }
+                if (ok) return B2F_OK;
+            }
         }
     }
     const int variant = (int)option("variant", 0);
@@ -646,6 +692,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
 extern "C" {
 
 int b2f_destroy_plan(b2f_plan pl) {
+    if (pl && pl->scratch) cudaFree(pl->scratch);
     delete pl;   // tables are cached library-wide
     return B2F_OK;
 }
@@ -661,6 +708,13 @@ int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
                  : st.type == STEP_CHIRP ? (st.inner > 1 ? "chirpz-strided" : "chirpz-contig") : "dense-matrix",
                  st.kind, st.axis, st.n_in, st.n_out, st.outer, st.inner,
                  st.src == BUF_IN ? "in" : "out", st.dst == BUF_IN ? "in" : "out");
+        s += line;
+    }
+    for (const RotPlanStep& r : pl->rot) {
+        char line[256];
+        static const char* nm[3] = {"in", "out", "scratch"};
+        snprintf(line, sizeof(line), "out-of-place alternative: stockham-rotating n=%d batches=%lld I=%lld O=%lld %s->%s\n",
+                 r.n, r.batches, r.I, r.O, nm[r.src], nm[r.dst]);
         s += line;
     }
     strncpy(buf, s.c_str(), buflen - 1);

@@ -196,6 +196,40 @@
 
 #define B2F_CPA_TABLE(X) B2F_CPA_TABLE_A(X) B2F_CPA_TABLE_B(X) B2F_CPA_TABLE_C(X)
 
+// rotating kernels (fft_rot.cuh): contiguous pencils in (bulk copies), rows of P
+// elements out with the axes rotated.  X(N, VAR, E, P, PS, STAGES, SPLIT, MINB + 16*OPT, radices...)
+// as B2F_TMA_TABLE, plus OPT bit 3 (MINB + 128): results leave through shared memory and TMA
+// stores, OPT bit 2 (MINB + 64): cp.async loader instead of bulk copies, OPT bits 4-5 (MINB + 256, + 512): 2 or 4 independent warp groups per CTA, each with
+// its own tile of P pencils; P * 16 bytes is the contiguous run of a STORE only (loads are
+// whole pencils whatever P is), so narrow tiles with two stages or two CTAs per SM
+// are candidates here.
+#define B2F_ROT_TABLE_A(X) \
+    X(64, 0, 8, 16, 30, 2, 0, 20, 8, 8) \
+    X(128, 0, 16, 16, 30, 2, 0, 18, 16, 8) \
+    X(128, 1, 16, 8, 30, 2, 0, 20, 16, 8) \
+    X(256, 0, 16, 8, 30, 2, 0, 18, 16, 16) \
+    X(256, 1, 16, 16, 30, 2, 0, 17, 16, 16) \
+    X(256, 2, 16, 8, 30, 3, 0, 17, 16, 16) \
+    X(256, 3, 16, 8, 30, 2, 0, 146, 16, 16) \
+    X(512, 0, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
+    X(512, 1, 32, 16, 5, 1, 1, 17, 32, 16) \
+    X(512, 2, 16, 4, 30, 2, 0, 18, 8, 8, 8) \
+    X(512, 3, 32, 8, 5, 2, 1, 17, 32, 16) \
+    X(512, 4, 32, 16, 5, 1, 1, 145, 32, 16) \
+    X(512, 5, 16, 8, 30, 2, 0, 145, 8, 8, 8)
+
+#define B2F_ROT_TABLE_B(X) \
+    X(1024, 0, 32, 8, 5, 1, 1, 17, 32, 32) \
+    X(1024, 1, 16, 8, 4, 1, 1, 17, 16, 8, 8) \
+    X(1024, 2, 32, 8, 5, 1, 1, 145, 32, 32) \
+    X(1024, 3, 32, 4, 5, 1, 1, 273, 32, 32) \
+    X(1024, 4, 32, 8, 5, 1, 1, 81, 32, 32) \
+    X(1024, 5, 32, 4, 5, 1, 1, 337, 32, 32) \
+    X(1024, 6, 16, 8, 4, 1, 1, 81, 16, 8, 8) \
+    X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
+
+#define B2F_ROT_TABLE(X) B2F_ROT_TABLE_A(X) B2F_ROT_TABLE_B(X)
+
 // real transforms (r2c / c2r of even length 2N through the N-point schedule,
 // fft_pow2.cuh fft_real_kernel):  X(N, E, P, PS, MINB, radices...), one row per N
 #define B2F_REAL_CONTIG_POW2(X)          \

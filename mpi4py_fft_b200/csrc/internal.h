@@ -52,6 +52,30 @@ cudaError_t launch_tma_f64(int n, int var, const TmaStep& st, cudaStream_t strea
 cudaError_t launch_tma_f32(int n, int var, const TmaStep& st, cudaStream_t stream);
 int sm_count();   // SMs of the current device (cached)
 
+// rotating c2c kernels (fft_rot_*.cu): transform the contiguous axis of in[b][i][o][n]
+// (pencil (i, o) of batch b starts at b*in_bstride + i*in_istride + o*in_ostride) and
+// store out[b][o][k][i] = out + b*out_bstride + o*out_ostride + k*out_nstride + i.
+// cudaErrorInvalidValue = (n, var) not built or pencils not 16-byte aligned.
+struct RotStep {
+    const void* in;
+    void* out;
+    long long batches, I, O;
+    long long in_istride, in_ostride, in_bstride;
+    long long out_ostride, out_nstride, out_bstride;
+    double scale;
+    int swap;
+    int grid_cap;
+};
+cudaError_t launch_rot_a_f64(int n, int var, const RotStep& st, cudaStream_t stream);
+cudaError_t launch_rot_b_f64(int n, int var, const RotStep& st, cudaStream_t stream);
+cudaError_t launch_rot_a_f32(int n, int var, const RotStep& st, cudaStream_t stream);
+cudaError_t launch_rot_b_f32(int n, int var, const RotStep& st, cudaStream_t stream);
+inline cudaError_t launch_rot(int precision, int n, int var, const RotStep& st, cudaStream_t stream) {
+    if (precision == 8) return n <= 512 ? launch_rot_a_f64(n, var, st, stream) : launch_rot_b_f64(n, var, st, stream);
+    return n <= 512 ? launch_rot_a_f32(n, var, st, stream) : launch_rot_b_f32(n, var, st, stream);
+}
+
+
 }  // namespace b2f
 struct b2f_plan_s;
 namespace b2f {

@@ -168,6 +168,7 @@ class Transform(object):
         self._all_transfers = self._transfer   # PFFT replaces this with the forward-order list (collective order)
         self._side = None                      # second stream of the pipelined redistribution
         self._plan = self._layout()
+        self._merged = self._merge()
 
     # -- arrays -------------------------------------------------------------------
     @property
@@ -242,6 +243,46 @@ class Transform(object):
                 if label not in ('IN', 'OUT'):
                     self._buffers.reserve(label, int(np.prod(shp)) * np.dtype(dt).itemsize)
         return dict(a=a, b=b, trivial=trivial, windowed=windowed)
+
+    def _merge(self):
+        """One planned transform over the axes of ALL stages, or None.
+
+        When no redistribution moves data (every transfer acts inside a group of one
+        rank: a single GPU, or axes that are not divided) and every stage is a plain
+        c2c stage on the same block, the chain is one multi-axis transform.  Handing it
+        to the library as such lets it run the rotating schedule (csrc/fft_rot.cuh:
+        whole-pencil bulk loads, page-local stores) instead of one strided pass per
+        axis; results are those of the stage-by-stage chain (c2c axes commute).  The
+        reference offers the same merge to the user as ``collapse=True``
+        (mpifft.py:255-272); here it is an execution detail, ``xfftn`` / ``transfer`` /
+        ``pencil`` keep the reference's structure."""
+        import os
+        from .fftw.utilities import FFTW_FORWARD, FFTW_BACKWARD
+        from .fftw.xfftn import FFT as Planned
+        from .libfft import _Stage
+        if os.environ.get('B2F_MERGE', '1') in ('0', 'false', 'no', ''):
+            return None
+        if len(self._xfftn) < 2 or not all(self._plan['trivial']):
+            return None
+        first = self._xfftn[0]
+        axes, kind = [], None
+        for st in self._xfftn:
+            if type(st) is not _Stage:
+                return None
+            pl = st._planned
+            if pl.kind not in (FFTW_FORWARD, FFTW_BACKWARD) or any(k != pl.kind for k in pl.kinds):
+                return None
+            if kind is not None and pl.kind != kind:
+                return None
+            kind = pl.kind
+            if tuple(st.input_shape) != tuple(first.input_shape) or tuple(st.output_shape) != tuple(first.input_shape) \
+                    or st.input_dtype != first.input_dtype or st.output_dtype != first.input_dtype:
+                return None
+            axes += [int(a) for a in pl.axes]
+        if len(set(axes)) != len(axes):
+            return None
+        spec = ArraySpec(first.input_shape, first.input_dtype)
+        return Planned(spec, ArraySpec(first.input_shape, first.input_dtype), axes, kind)
 
     # -- execution -------------------------------------------------------------------
     def _fused(self, i, st, tr, direction):
@@ -365,6 +406,15 @@ class Transform(object):
             # a multi-axis c2r stage overwrites what it reads: keep the caller's array intact
             self.input_array[...] = src
             src = self.input_array
+        if self._merged is not None:
+            scale = 1.0
+            for st in self._xfftn:
+                scale *= st.scale_for(kw.get('normalize'))
+            self._merged.execute(src, out, scale)
+            if output_array is not None and not direct_out:
+                _copy_out(out, output_array)
+                return output_array
+            return out
         cur = src
         skip = -1
         for i in range(m):
@@ -632,6 +682,9 @@ class PFFT(object):
             t.destroy()
         for s in self.xfftn:
             s.destroy()
+        for tr in (self.forward, self.backward):
+            if tr._merged is not None:
+                tr._merged.destroy()
 
     def shape(self, forward_output=True):
         """Local shape: spectral space if ``forward_output`` else physical."""

@@ -94,7 +94,7 @@ def emu():
     so = os.path.join(ROOT, 'tests', 'emu', 'libemu_fft.so')
     src = os.path.join(ROOT, 'tests', 'emu', 'emu_fft.cpp')
     deps = [src] + [os.path.join(ROOT, 'mpi4py_fft_b200', 'csrc', f)
-                    for f in ('fft_core.cuh', 'fft_pow2.cuh', 'fft_tma.cuh', 'fft_configs.h', 'transfer_put.h', 'chirpz.cuh', 'chirpz_host.h')]
+                    for f in ('fft_core.cuh', 'fft_pow2.cuh', 'fft_tma.cuh', 'fft_configs.h', 'transfer_put.h', 'chirpz.cuh', 'chirpz_host.h', 'fft_rot.cuh', 'rot_plan.h')]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(['g++', '-std=c++17', '-O1', '-shared', '-fPIC', '-o', so, src])
     lib = ctypes.CDLL(so)

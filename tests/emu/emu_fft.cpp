@@ -678,3 +678,107 @@ extern "C" int emu_fft_scatter_chunk(int precision, int ndims, const long long* 
     if (precision == 8) return emu_dispatch<double>(n, 0, strided, prm, outer);
     return emu_dispatch<float>(n, 0, strided, prm, outer);
 }
+
+// ---- rotating kernels (fft_rot.cuh) stepped on the CPU: the bulk copies are
+// emulated by memcpy of whole pencils into the padded stage, everything after is
+// the kernel's own per-thread code; the schedule (which strides each of the three
+// steps uses) is the library's own build_rotation (rot_plan.h).
+#include "../../mpi4py_fft_b200/csrc/fft_rot.cuh"
+#include "../../mpi4py_fft_b200/csrc/rot_plan.h"
+
+struct EmuRotStep {
+    const void* in;
+    void* out;
+    long long batches, I, O, in_i, in_o, in_b, out_o, out_n, out_b;
+    double scale;
+    int swap;
+};
+
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int OPT>
+static int emu_rot_one(const EmuRotStep& st) {
+    using TF = TileFFT<T, N, E, RAD, P, true, PS>;
+    using EX = Exchange<TF, SPLIT>;
+    using C = cplx<T>;
+    constexpr int PITCH = N + RotPad<T, P>::value;
+    const long long tpo = (st.I + P - 1) / P, tpb = st.O * tpo, ntiles = st.batches * tpb;
+    std::vector<C> twv((size_t)RAD::tw_total());
+    build_pass_twiddles<T, RAD>(twv.data());
+    std::vector<C> stage((size_t)PITCH * P);
+    std::vector<typename EX::X> xbuf((size_t)TF::SI::tile_elems);
+    std::vector<C> regs((size_t)TF::THREADS * E);
+    const C* gin = reinterpret_cast<const C*>(st.in);
+    C* gout = reinterpret_cast<C*>(st.out);
+    for (long long t = 0; t < ntiles; ++t) {
+        const long long b = t / tpb, rem = t - b * tpb, o = rem / tpo, i0 = (rem - o * tpo) * P;
+        for (auto& x : stage) { x.x = (T)1e30; x.y = (T)-1e30; }
+        for (int j = 0; j < P && i0 + j < st.I; ++j)
+            std::memcpy(&stage[(size_t)j * PITCH], gin + b * st.in_b + o * st.in_o + (i0 + j) * st.in_i, sizeof(C) * N);
+        for (int tid = 0; tid < TF::THREADS; ++tid)
+            load_rows<TF, PITCH>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), stage.data(), st.swap != 0);
+        for (auto& x : xbuf) x = typename EX::X{};
+        for (int tid = 0; tid < TF::THREADS; ++tid)
+            TF::template twiddle_dft<0>(&regs[(size_t)tid * E], TF::slot_of(tid), twv.data());
+        EmuTmaMid<TF, EX, 1>::run(regs, xbuf.data(), twv.data(), SPLIT);
+        if constexpr ((OPT & 8) != 0) {
+            // TMA-store flavour: chunks of rows staged in the exchange buffer, then box stores
+            // (emulated by a dense copy clipped at the tensor's extent I)
+            using OC = OutChunks<TF, EX>;
+            C* xo = reinterpret_cast<C*>(xbuf.data());
+            static_assert(sizeof(typename EX::X) * TF::SI::tile_elems >= sizeof(C) * (size_t)OC::rows * P, "staging fits");
+            for (int c = 0; c < OC::count; ++c) {
+                // __syncthreads()
+                for (int k = 0; k < OC::rows * P; ++k) { xo[k].x = (T)1e30; xo[k].y = (T)-1e30; }
+                for (int tid = 0; tid < TF::THREADS; ++tid)
+                    stage_out_rows<TF, OC::count>(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), xo, c,
+                                                  st.swap != 0, (T)st.scale);
+                // __syncthreads(); boxes of box_rows rows
+                for (int k = 0; k < OC::rows; ++k)
+                    for (int pp = 0; pp < P && i0 + pp < st.I; ++pp)
+                        gout[b * st.out_b + o * st.out_o + (long long)(c * OC::rows + k) * st.out_n + i0 + pp] = xo[(size_t)k * P + pp];
+            }
+        } else {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                const long long i = i0 + TF::pencil_of(tid);
+                TF::store_global(&regs[(size_t)tid * E], TF::slot_of(tid), gout + b * st.out_b + o * st.out_o + i, st.out_n,
+                                 i < st.I, st.swap != 0, (T)st.scale);
+            }
+        }
+    }
+    return 0;
+}
+
+#define EMU_ROT(N, VAR, E, P, PS, STAGES, SPLIT, MINB, ...) \
+    if (n == N && var == VAR)                                \
+        return emu_rot_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), PS, STAGES, SPLIT != 0, ((MINB) >> 4)>(st);
+
+template <class T>
+static int emu_rot_dispatch(int n, int var, const EmuRotStep& st) {
+    B2F_ROT_TABLE(EMU_ROT)
+    return -1;
+}
+
+// the whole 3-step schedule of a block (ndims >= 3, axes = its last three in any order);
+// var < 0: the default variant of each length.  -1: schedule does not apply / variant not built.
+extern "C" int emu_rot_plan(int precision, int ndims, const long long* sizes, const int* axes, int var, const void* in,
+                            void* out, void* scratch, double scale, int swap) {
+    std::vector<RotPlanStep> steps;
+    long long elems = 0;
+    if (!build_rotation(ndims, sizes, axes, 3, &steps, &elems)) return -1;
+    void* bufs[3] = {const_cast<void*>(in), out, scratch};
+    for (size_t si = 0; si < steps.size(); ++si) {
+        const RotPlanStep& r = steps[si];
+        EmuRotStep st{bufs[r.src], bufs[r.dst], r.batches, r.I, r.O, r.in_i, r.in_o, r.in_b, r.out_o, r.out_n, r.out_b,
+                      si + 1 == steps.size() ? scale : 1.0, swap};
+        const int v = var >= 0 ? var : rot_default(r.n);
+        const int rc = precision == 8 ? emu_rot_dispatch<double>(r.n, v, st) : emu_rot_dispatch<float>(r.n, v, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// one rotating step on its own: in [B][I][O][n] -> out [B][O][n][I]
+extern "C" int emu_rot_step(int precision, int n, int var, long long batches, long long I, long long O, const void* in,
+                            void* out, double scale, int swap) {
+    EmuRotStep st{in, out, batches, I, O, O * n, n, I * O * n, (long long)n * I, I, I * O * n, scale, swap};
+    return precision == 8 ? emu_rot_dispatch<double>(n, var, st) : emu_rot_dispatch<float>(n, var, st);
+}
