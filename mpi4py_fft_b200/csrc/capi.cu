@@ -490,8 +490,37 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                     RotStep rs{bufs[r.src], bufs[r.dst], r.batches, r.I, r.O, r.in_i, r.in_o, r.in_b,
                                r.out_o, r.out_n, r.out_b, si + 1 == pl->rot.size() ? scale : 1.0,
                                pl->rot_swap ? 1 : 0, 0};
-                    cudaError_t e = launch_rot(pl->precision, r.n, vr >= 0 ? vr : rot_default(r.n), rs, st);
-                    if (e == cudaErrorInvalidValue && vr >= 0) e = launch_rot(pl->precision, r.n, rot_default(r.n), rs, st);
+                    cudaError_t e;
+                    if (vr >= 1000) {
+                        // register-path engine: the strided kernels with whole pencils in, rotated rows out
+                        FftParams prm;
+                        memset(&prm, 0, sizeof(prm));
+                        prm.scale = rs.scale;
+                        prm.swap = rs.swap;
+                        prm.in_ostride = r.in_o;
+                        prm.out_ostride = r.out_o;
+                        prm.in_nstride = 1;
+                        prm.out_nstride = r.out_n;
+                        prm.in_istride = r.in_i;
+                        prm.inner = r.I;
+                        e = cudaSuccess;
+                        for (long long b = 0; b < r.batches && e == cudaSuccess; ++b) {
+                            prm.in = (const char*)rs.in + b * r.in_b * 2 * pl->precision;
+                            prm.out = (char*)rs.out + b * r.out_b * 2 * pl->precision;
+                            const int v = vr - 1000;
+                            if (pl->precision == 8)
+                                e = r.n <= 256 ? launch_pow2_small_f64(r.n, v, true, prm, r.O, st)
+                                  : r.n <= 1024 ? launch_pow2_mid_f64(r.n, v, true, prm, r.O, st)
+                                                : launch_pow2_large_f64(r.n, v, true, prm, r.O, st);
+                            else
+                                e = r.n <= 256 ? launch_pow2_small_f32(r.n, v, true, prm, r.O, st)
+                                  : r.n <= 1024 ? launch_pow2_mid_f32(r.n, v, true, prm, r.O, st)
+                                                : launch_pow2_large_f32(r.n, v, true, prm, r.O, st);
+                        }
+                    } else {
+                        e = launch_rot(pl->precision, r.n, vr >= 0 ? vr : rot_default(r.n), rs, st);
+                        if (e == cudaErrorInvalidValue && vr >= 0) e = launch_rot(pl->precision, r.n, rot_default(r.n), rs, st);
+                    }
                     if (e != cudaSuccess) return cuda_fail(e, "b2f_execute: rotating kernel launch");
                 }
                 if (ok) return B2F_OK;

@@ -73,7 +73,10 @@
     X(1024, 1, 16, 4, 4, 2, 16, 8, 8)     \
     X(1024, 2, 32, 8, 30, 1, 32, 32)      \
     X(1024, 3, 32, 4, 5, 1, 32, 32)       \
-    X(1024, 4, 16, 4, 4, 1, 16, 8, 8)
+    X(1024, 4, 16, 4, 4, 1, 16, 8, 8)     \
+    X(1024, 5, 16, 2, 4, 4, 16, 8, 8)     \
+    X(1024, 6, 16, 4, 4, 3, 16, 8, 8)     \
+    X(1024, 7, 16, 1, 4, 8, 16, 8, 8)
 
 #define B2F_CONTIG_LARGE(X)               \
     X(2048, 0, 16, 2, 4, 1, 16, 16, 8)    \

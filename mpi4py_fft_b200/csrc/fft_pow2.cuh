@@ -23,6 +23,8 @@ struct FftParams {
     long long out_ostride;
     long long in_nstride;    // elements between consecutive points of a pencil (STRIDED)
     long long out_nstride;
+    long long in_istride;    // STRIDED: elements between consecutive inner indices on the INPUT side (0 = 1: the
+                             // plain layout; > 1 with in_nstride = 1: whole pencils in, rotated rows out, rot_plan.h)
     long long inner;         // STRIDED: extent of the contiguous inner index
     long long npencils;      // CONTIG: number of rows
     long long tiles_per_outer;
@@ -73,7 +75,7 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
         const long long o = bid / prm.tiles_per_outer;
         const long long i = (bid - o * prm.tiles_per_outer) * P + p;
         valid = i < prm.inner;
-        gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+        gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + (prm.in_istride ? i * prm.in_istride : i);
         gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
         in_ns = prm.in_nstride;
         out_ns = prm.out_nstride;

@@ -169,6 +169,7 @@ class Transform(object):
         self._side = None                      # second stream of the pipelined redistribution
         self._plan = self._layout()
         self._merged = self._merge()
+        self._marks = None                     # profiling: a list collects (stage indices, CUDA event) per stage
 
     # -- arrays -------------------------------------------------------------------
     @property
@@ -406,11 +407,16 @@ class Transform(object):
             # a multi-axis c2r stage overwrites what it reads: keep the caller's array intact
             self.input_array[...] = src
             src = self.input_array
+        marks = self._marks
+        if marks is not None:
+            marks.append(((), _mark()))
         if self._merged is not None:
             scale = 1.0
             for st in self._xfftn:
                 scale *= st.scale_for(kw.get('normalize'))
             self._merged.execute(src, out, scale)
+            if marks is not None:
+                marks.append((tuple(range(m)), _mark()))
             if output_array is not None and not direct_out:
                 _copy_out(out, output_array)
                 return output_array
@@ -439,6 +445,8 @@ class Transform(object):
                         self._run_pipelined(i, chunks, cur, recv, dst2, tr, direction, table[label], kw.get('normalize'))
                         cur = dst2
                         skip = i + 1
+                        if marks is not None:
+                            marks.append(((i, i + 1), _mark()))
                         continue
                     if self._fused(i, st, tr, direction):
                         # one launch: the stage's last pass stores into the owners' windows
@@ -453,11 +461,21 @@ class Transform(object):
             else:
                 st.run(cur, dst, kw.get('normalize'))
                 cur = dst
+            if marks is not None:
+                marks.append(((i,), _mark()))
 
         if output_array is not None and not direct_out:
             _copy_out(out, output_array)
             return output_array
         return out
+
+
+def _mark():
+    """timing event on the current stream (Transform._marks)"""
+    import torch
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record(torch.cuda.current_stream())
+    return ev
 
 
 def p2p_enabled():

@@ -71,7 +71,7 @@ static int emu_one(const FftParams& prm_in, long long outer) {
                 const long long o = bid / prm.tiles_per_outer;
                 const long long i = (bid - o * prm.tiles_per_outer) * P + p;
                 L.valid = i < prm.inner;
-                L.gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+                L.gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + (prm.in_istride ? i * prm.in_istride : i);
                 L.gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
                 L.in_ns = prm.in_nstride;
                 L.out_ns = prm.out_nstride;
@@ -769,8 +769,30 @@ extern "C" int emu_rot_plan(int precision, int ndims, const long long* sizes, co
         const RotPlanStep& r = steps[si];
         EmuRotStep st{bufs[r.src], bufs[r.dst], r.batches, r.I, r.O, r.in_i, r.in_o, r.in_b, r.out_o, r.out_n, r.out_b,
                       si + 1 == steps.size() ? scale : 1.0, swap};
-        const int v = var >= 0 ? var : rot_default(r.n);
-        const int rc = precision == 8 ? emu_rot_dispatch<double>(r.n, v, st) : emu_rot_dispatch<float>(r.n, v, st);
+        int rc;
+        if (var >= 1000) {
+            // register-path engine: the strided kernels with whole pencils in (in_istride), rows out
+            FftParams prm;
+            std::memset(&prm, 0, sizeof(prm));
+            prm.scale = st.scale;
+            prm.swap = swap;
+            prm.in_ostride = r.in_o;
+            prm.out_ostride = r.out_o;
+            prm.in_nstride = 1;
+            prm.out_nstride = r.out_n;
+            prm.in_istride = r.in_i;
+            prm.inner = r.I;
+            rc = 0;
+            for (long long b = 0; b < r.batches && rc == 0; ++b) {
+                prm.in = (const char*)st.in + b * r.in_b * 2 * precision;
+                prm.out = (char*)st.out + b * r.out_b * 2 * precision;
+                rc = precision == 8 ? emu_dispatch<double>(r.n, var - 1000, true, prm, r.O)
+                                    : emu_dispatch<float>(r.n, var - 1000, true, prm, r.O);
+            }
+        } else {
+            const int v = var >= 0 ? var : rot_default(r.n);
+            rc = precision == 8 ? emu_rot_dispatch<double>(r.n, v, st) : emu_rot_dispatch<float>(r.n, v, st);
+        }
         if (rc) return rc;
     }
     return 0;

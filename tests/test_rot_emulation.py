@@ -54,12 +54,14 @@ def test_rot_schedule_is_fftn(emu, shape, axes, prec):
     x = (rng.random(shape) + 1j * rng.random(shape)).astype(ct)
     sizes = (C.c_longlong * len(shape))(*shape)
     ax = (C.c_int * 3)(*axes)
-    for swap in (0, 1):
+    # engine: -1 = bulk-copy staged rotating kernels, 1000 = the strided register-path kernels
+    # with whole pencils in (FftParams::in_istride)
+    for swap, var in ((0, -1), (1, -1), (0, 1000), (1, 1000)):
         y = np.full(shape, np.nan, dtype=ct)
         w = np.full(shape, np.nan, dtype=ct)
         xin = x.copy()
         scale = 0.5
-        rc = emu.emu_rot_plan(prec, len(shape), sizes, ax, -1, xin.ctypes.data, y.ctypes.data, w.ctypes.data,
+        rc = emu.emu_rot_plan(prec, len(shape), sizes, ax, var, xin.ctypes.data, y.ctypes.data, w.ctypes.data,
                               C.c_double(scale), swap)
         assert rc == 0
         assert np.array_equal(xin, x)          # the input survives

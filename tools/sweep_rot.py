@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--variants', default='0-4')
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--backward', action='store_true')
+    ap.add_argument('--steps', default='0', help='which single steps to time alone (0,1,2)')
     args = ap.parse_args()
     import torch
     import mpi4py_fft_b200 as B
@@ -78,7 +79,7 @@ def main():
             print("var %d: %s" % (var, str(exc)[:100]))
             continue
         print("rot var %d  all 3 steps    %8.3f ms  %7.1f GB/s per axis avg  %.3f" % (var, ms, 3 * nbytes / ms / 1e6, 3 * nbytes / ms / 1e6 / peak), flush=True)
-        for k in range(3):
+        for k in [int(x) for x in args.steps.split(',') if x != '']:
             _lib.set_option('rot_step_mask', 1 << k)
             ms = timeit(plan)
             gbs = nbytes / ms / 1e6
