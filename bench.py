@@ -347,8 +347,9 @@ def fill_plane_waves(torch, u_t, local_slice, shape, real, ks, amps, rows=None):
     for k in ks:
         f = []
         for ax in range(nd):
-            idx = torch.arange(starts[ax], starts[ax] + u_t.shape[ax], device=u_t.device, dtype=torch.float64)
-            ph = (2.0 * np.pi * k[ax] / shape[ax]) * idx
+            # exact phase reduction in integers: (k * x) mod n, so that cos / sin see an argument below 2 pi
+            idx = torch.arange(starts[ax], starts[ax] + u_t.shape[ax], device=u_t.device, dtype=torch.int64)
+            ph = ((idx * int(k[ax])) % int(shape[ax])).to(torch.float64) * (2.0 * np.pi / shape[ax])
             f.append(torch.complex(torch.cos(ph), torch.sin(ph)).to(cdt))
         facs.append(f)
     for lo in range(0, n0, rows):
@@ -496,7 +497,7 @@ def run_b200(args):
         desc = merged.plan().describe().strip().split('\n')
         rot = [ln for ln in desc if 'rotating' in ln]
         classic = [ln for ln in desc if 'rotating' not in ln]
-        if rot and _lib.lib().b2f_get_option(b'rotate') != 0:
+        if rot and os.environ.get('B2F_ROTATE', '0') not in ('0', ''):
             how = "each kernel of the rotating schedule alone (option rot_step_mask), arrays of the timed step"
             for k, ln in enumerate(rot):
                 _lib.set_option('rot_step_mask', 1 << k)

@@ -173,6 +173,16 @@ B2F_API int b2f_ipc_close(void *d_peer);
 B2F_API int b2f_transfer_put(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
 B2F_API int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void *d_src, void *const *peer_dst, void *stream);
 
+/* Group barrier of the peer-memory path without NCCL: peer_flags[j] = the array of nranks
+ * 64-bit arrival counters owned by group rank j (zeroed, in IPC-exported memory such as
+ * b2f_malloc's) as mapped in THIS process, peer_flags[rank] = the local one.  Once set,
+ * b2f_transfer_exchange_p2p / b2f_execute_scatter(_chunk) order the ranks with one tiny
+ * kernel (st.release.sys / ld.acquire.sys on the counters over NVLink) instead of a 1-int
+ * ncclAllReduce; NULL returns to NCCL.  b2f_transfer_barrier enqueues the barrier alone.
+ * Replaces the synchronisation implied by the blocking MPI_Alltoallw (pencil.py:182,200). */
+B2F_API int b2f_transfer_set_flags(b2f_transfer t, void *const *peer_flags);
+B2F_API int b2f_transfer_barrier(b2f_transfer t, void *stream);
+
 /* ---- (1)+(2) fused: the stage's last pass stores into the owners' windows ----
  * out = scale * T(in), but the last butterfly pass of the stage writes every
  * point straight into the array of the rank that owns it after transfer `t`

@@ -49,6 +49,8 @@ SYMBOLS = {
     'b2f_ipc_close': (C.c_int, [C.c_void_p]),
     'b2f_transfer_put': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     'b2f_transfer_exchange_p2p': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    'b2f_transfer_set_flags': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'b2f_transfer_barrier': (C.c_int, [C.c_void_p, C.c_void_p]),
     'b2f_execute_chunk': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int64, C.c_int64,
                                     C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     'b2f_execute_scatter_chunk': (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
@@ -270,6 +272,18 @@ class TransferHandle(object):
         arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         check(lib().b2f_transfer_exchange_p2p(self._h, int(direction), C.c_void_p(device_ptr(src)), arr,
                                               current_stream_ptr()), 'b2f_transfer_exchange_p2p')
+
+    def set_flags(self, peer_flag_ptrs):
+        """arrival counters of every group rank as mapped here: the group barrier of the
+        peer-memory path becomes one small kernel instead of an NCCL all-reduce"""
+        if peer_flag_ptrs is None:
+            check(lib().b2f_transfer_set_flags(self._h, None), 'b2f_transfer_set_flags')
+            return
+        arr = (C.c_void_p * len(peer_flag_ptrs))(*[int(p) for p in peer_flag_ptrs])
+        check(lib().b2f_transfer_set_flags(self._h, arr), 'b2f_transfer_set_flags')
+
+    def barrier(self):
+        check(lib().b2f_transfer_barrier(self._h, current_stream_ptr()), 'b2f_transfer_barrier')
 
     def pack(self, direction, src, packed):
         from .devarray import device_ptr

@@ -379,7 +379,7 @@ int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int6
         // splits -- and only the last step can store into the peers' windows
         for (int i = 0; i < naxes && rc == B2F_OK; ++i)
             rc = add_step(pl, k0, ax[i], pl->sizes_in, pl->sizes_out, 2, 2, i == 0 ? BUF_IN : BUF_OUT, BUF_OUT);
-        if (rc == B2F_OK && option("rotate", 1)) {
+        if (rc == B2F_OK) {
             long long elems = 0;
             if (build_rotation(ndims, pl->sizes_in.data(), ax.data(), naxes, &pl->rot, &elems))
                 pl->scratch_bytes = (size_t)elems * 2 * precision;
@@ -464,7 +464,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             return B2F_EUNSUPPORTED;
         }
     }
-    if (!pl->rot.empty() && !peer_last && !before_last && !(chunk && chunk->mode != 0) && option("rotate", 1)) {
+    if (!pl->rot.empty() && !peer_last && !before_last && !(chunk && chunk->mode != 0) && option("rotate", 0)) {
         // out of place and not overlapping: the first step writes d_out while d_in is still being read
         const char* a = (const char*)d_in;
         const char* b = (const char*)d_out;

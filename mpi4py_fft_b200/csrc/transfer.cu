@@ -246,6 +246,12 @@ struct b2f_comm_s {
 
 struct b2f_transfer_s {
     b2f_comm comm;
+    // flag barrier over peer memory (b2f_transfer_set_flags): flags[j] points at the
+    // nranks 64-bit arrival counters of group rank j (my own array for j == rank), as
+    // mapped in this process; epoch counts the barriers this transfer has enqueued
+    unsigned long long* flags[B2F_MAX_PEERS] = {};
+    unsigned long long epoch = 0;
+    bool has_flags = false;
     int nranks, rank, ndims, itemsize;
     std::vector<long long> shape, subA, subB;
     int axisA, axisB;
@@ -512,12 +518,60 @@ static int build_put(b2f_transfer t, int direction, const void* d_src, void* con
     return B2F_OK;
 }
 
-// stream-ordered barrier over the group: a 1-int all-reduce.  When it completes on
-// this rank's stream every peer has reached it on its own stream, i.e. everything
-// the peers enqueued before it (their kernels reading or writing the windows) is done.
-static int group_barrier(b2f_comm c, cudaStream_t st) {
+// Stream-ordered barrier over the group.  When it completes on this rank's stream every
+// peer has reached it on its own stream, i.e. everything the peers enqueued before it
+// (their kernels reading or writing the windows) is done.
+//
+// Flag form (default once the peers' flag arrays are mapped): one tiny kernel; thread j
+// publishes this rank's arrival count in peer j's array (st.release.sys over NVLink) and
+// spins on the count peer j left here (ld.acquire.sys).  No NCCL kernel, no proxy thread:
+// a few microseconds instead of an all-reduce launch, which matters once a redistribution
+// is cut into chunks with a barrier each.  Counts only grow (epoch = number of barriers of
+// this transfer so far, the same on every rank because barriers are enqueued collectively).
+struct FlagBarrier {
+    unsigned long long* flags[B2F_MAX_PEERS];
+    unsigned long long epoch;
+    int p, rank;
+};
+__global__ void __launch_bounds__(32) flag_barrier_kernel(const FlagBarrier fb) {
+    const int j = threadIdx.x;
+    __threadfence_system();
+    if (j < fb.p && j != fb.rank) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fb.flags[j] + fb.rank), "l"(fb.epoch) : "memory");
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fb.flags[fb.rank] + j) : "memory");
+        } while (seen < fb.epoch);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// Fallback: a 1-int all-reduce on the group's NCCL communicator.
+static int nccl_barrier(b2f_comm c, cudaStream_t st) {
     ncclResult_t r = g_nccl.AllReduce(c->d_flag, c->d_flag + 1, 1, ncclInt32, ncclSum, c->comm, st);
     return r == ncclSuccess ? B2F_OK : nccl_fail(r, "ncclAllReduce(barrier)");
+}
+
+static int group_barrier(b2f_transfer t, cudaStream_t st) {
+    if (t->has_flags && option("flag_barrier", 1)) {
+        FlagBarrier fb;
+        for (int j = 0; j < t->nranks; ++j) fb.flags[j] = t->flags[j];
+        fb.epoch = ++t->epoch;
+        fb.p = t->nranks;
+        fb.rank = t->rank;
+        flag_barrier_kernel<<<1, 32, 0, st>>>(fb);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? B2F_OK : cuda_fail(e, "flag barrier kernel");
+    }
+    if (!t->comm) {
+        set_error("transfer has neither peer flags nor a communicator for its group barrier");
+        return B2F_EINVAL;
+    }
+    int rc = need_nccl();
+    if (rc) return rc;
+    return nccl_barrier(t->comm, st);
 }
 
 extern "C" {
@@ -597,7 +651,7 @@ static int build_peer_store(b2f_transfer t, int direction, b2f_plan plan, void* 
     return B2F_OK;
 }
 
-static int barrier_hook(void* ctx, cudaStream_t st) { return group_barrier((b2f_comm)ctx, st); }
+static int barrier_hook(void* ctx, cudaStream_t st) { return group_barrier((b2f_transfer)ctx, st); }
 
 static int execute_scatter_impl(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t,
                                 int direction, void* const* peer_dst, int sync_flags, const ChunkSpec* chunk,
@@ -612,18 +666,15 @@ static int execute_scatter_impl(b2f_plan plan, const void* d_in, void* d_work, d
     cudaStream_t st = (cudaStream_t)stream;
     const bool multi = t->nranks > 1;
     const bool enter = multi && (sync_flags & 1), leave = multi && (sync_flags & 2);
-    if (enter || leave) {
-        if (!t->comm) {
-            set_error("transfer was created without a communicator");
-            return B2F_EINVAL;
-        }
-        if ((rc = need_nccl())) return rc;
+    if ((enter || leave) && !t->has_flags && !t->comm) {
+        set_error("transfer was created without a communicator");
+        return B2F_EINVAL;
     }
     // d_work receives the intermediate of a multi-axis stage; a single-step stage never touches it
     rc = run_plan(plan, d_in, d_work ? d_work : const_cast<void*>(d_in), scale, st, &ps,
-                  enter ? barrier_hook : nullptr, enter ? (void*)t->comm : nullptr, chunk);
+                  enter ? barrier_hook : nullptr, enter ? (void*)t : nullptr, chunk);
     if (rc) return rc;
-    return leave ? group_barrier(t->comm, st) : B2F_OK;
+    return leave ? group_barrier(t, st) : B2F_OK;
 }
 
 int b2f_execute_scatter(b2f_plan plan, const void* d_in, void* d_work, double scale, b2f_transfer t, int direction,
@@ -636,6 +687,34 @@ int b2f_execute_scatter_chunk(b2f_plan plan, const void* d_in, double scale, b2f
                               int64_t view_outer, int64_t view_ostride, int grid_cap, void* stream) {
     ChunkSpec ch{mode, begin, count, view_outer, view_ostride, grid_cap};
     return execute_scatter_impl(plan, d_in, nullptr, scale, t, direction, peer_dst, sync_flags, &ch, stream);
+}
+
+int b2f_transfer_set_flags(b2f_transfer t, void* const* peer_flags) {
+    if (!t) return B2F_EINVAL;
+    if (!peer_flags) {
+        t->has_flags = false;
+        return B2F_OK;
+    }
+    if (t->nranks > B2F_MAX_PEERS) {
+        set_error("flag barrier supports groups of up to " + std::to_string(B2F_MAX_PEERS) + " ranks");
+        return B2F_EUNSUPPORTED;
+    }
+    for (int j = 0; j < t->nranks; ++j) {
+        if (!peer_flags[j] || ((uintptr_t)peer_flags[j] & 7)) {
+            set_error("b2f_transfer_set_flags: null or misaligned flag array");
+            return B2F_EINVAL;
+        }
+        t->flags[j] = reinterpret_cast<unsigned long long*>(peer_flags[j]);
+    }
+    t->epoch = 0;
+    t->has_flags = true;
+    return B2F_OK;
+}
+
+int b2f_transfer_barrier(b2f_transfer t, void* stream) {
+    if (!t) return B2F_EINVAL;
+    if (t->nranks == 1) return B2F_OK;
+    return group_barrier(t, (cudaStream_t)stream);
 }
 
 int b2f_plan_can_scatter(b2f_plan plan, b2f_transfer t, int direction) {
@@ -652,18 +731,17 @@ int b2f_transfer_exchange_p2p(b2f_transfer t, int direction, const void* d_src, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (t->nranks == 1) return b2f_transfer_put(t, direction, d_src, peer_dst, stream);
-    if (!t->comm) {
+    if (!t->has_flags && !t->comm) {
         set_error("transfer was created without a communicator");
         return B2F_EINVAL;
     }
-    int rc = need_nccl();
-    if (rc) return rc;
+    int rc;
     PutParams prm;
     if ((rc = build_put(t, direction, d_src, peer_dst, &prm))) return rc;
-    if ((rc = group_barrier(t->comm, st))) return rc;      // the peers are done with their windows
+    if ((rc = group_barrier(t, st))) return rc;      // the peers are done with their windows
     cudaError_t e = launch_put(prm, st);
     if (e != cudaSuccess) return cuda_fail(e, "put kernel");
-    return group_barrier(t->comm, st);                      // every block has landed in my window
+    return group_barrier(t, st);                      // every block has landed in my window
 }
 
 }  // extern "C"

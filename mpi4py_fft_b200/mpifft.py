@@ -26,6 +26,11 @@ from .libfft import FFT
 from .pencil import Pencil, Subcomm
 
 
+_SYNC = '__sync__'       # window holding the arrival counters of the flag barriers
+_SYNC_SLOT = 128         # bytes per transfer: 16 ranks x 8-byte counter
+_MAX_PEERS = 16          # B2F_MAX_PEERS / B2F_PUT_MAX_PEERS of the kernels
+
+
 class _Buffers(object):
     """End-point arrays X (physical) / Y (spectral) and two byte work buffers,
     shared by the forward and backward transforms of one PFFT; all lazy."""
@@ -57,13 +62,24 @@ class _Buffers(object):
                 w = _lib.Window(nbytes)
                 self.windows[label] = w
                 handles[label] = w.handle()
+            # arrival counters of the flag barrier: 16 x 8 bytes per transfer, zeroed before anybody maps them
+            import torch
+            w = _lib.Window(_SYNC_SLOT * max(1, len(transfers)))
+            w.tensor.zero_()
+            torch.cuda.synchronize()
+            self.windows[_SYNC] = w
+            handles[_SYNC] = w.handle()
         except Exception as exc:   # e.g. IPC not permitted in this container
             ok = False
             handles = {'error': repr(exc)[:200]}
         opened = {}
-        for t in transfers:
+        for ti, t in enumerate(transfers):
             comm = t.comm
             if comm.Get_size() == 1:
+                continue
+            if comm.Get_size() > _MAX_PEERS:
+                # the peer-store and put kernels address at most 16 owners: larger groups keep pack + NCCL + unpack
+                self.peers[id(t)] = None
                 continue
             everyone = comm.allgather((ok, handles))
             me = comm.Get_rank()
@@ -88,6 +104,9 @@ class _Buffers(object):
             # the decision must be the same on every rank of the group
             agreed = all(comm.allgather(table is not None))
             self.peers[id(t)] = table if agreed else None
+            if agreed and flag_barrier_enabled():
+                # group barrier = one small kernel on counters in peer memory instead of an NCCL all-reduce
+                t._plan().set_flags([ptr + ti * _SYNC_SLOT for ptr in table[_SYNC]])
             if not agreed and me == 0:
                 import warnings
                 reasons = [e[1].get('error') for e in everyone if isinstance(e[1], dict) and e[1].get('error')]
@@ -512,6 +531,12 @@ def pipeline_producer_sms(p):
     if env:
         return int(env)
     return int(min(120, max(32, round(148 * 0.30 * p / (p - 1)))))
+
+
+def flag_barrier_enabled():
+    """Group barriers of the peer-memory path as flag kernels (B2F_FLAG_BARRIER=0: NCCL all-reduce)."""
+    import os
+    return os.environ.get('B2F_FLAG_BARRIER', '1') not in ('0', 'false', 'no', '')
 
 
 def fused_enabled():

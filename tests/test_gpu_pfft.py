@@ -619,3 +619,67 @@ def test_full_size_c2_properties(B):
     w.tensor.copy_(2.5 * u.tensor - 0.5j * v.tensor)
     wh = fft.forward(w)
     assert float((wh.tensor - (2.5 * uh_copy - 0.5j * vh)).abs().max().item()) < 1e-12
+
+
+@pytest.mark.parametrize('p', [2, 3, 4])     # one hardware queue per played rank (8 by default): a spinning kernel must never sit in front of a peer's
+def test_flag_barrier_orders_ranks_played_on_streams(B, p):
+    """b2f_transfer_set_flags / b2f_transfer_barrier with every rank of a group played on one
+    device, one CUDA stream per rank: a rank's writes enqueued BEFORE its barrier are seen by
+    every peer's reads enqueued AFTER theirs (the ordering MPI_Alltoallw's blocking semantics
+    give the reference, pencil.py:182,200) -- exchange_p2p with flags = the put kernel between
+    two such barriers, no NCCL communicator involved."""
+    import torch
+    from mpi4py_fft_b200._lib import TransferHandle
+    from mpi4py_fft_b200.devarray import device_ptr
+    from mpi4py_fft_b200.pencil import _blockdist
+    shape, axisA, axisB = (4 * p, 3 * p, 40), 1, 0
+    g = rand(shape, 'D', 5)
+
+    def blocks(axis_split):
+        out = []
+        for r in range(p):
+            n, s0 = _blockdist(shape[axis_split], p, r)
+            sl = [slice(None)] * len(shape)
+            sl[axis_split] = slice(s0, s0 + n)
+            out.append(np.ascontiguousarray(g[tuple(sl)]))
+        return out
+    A, Bx = blocks(axisB), blocks(axisA)
+    flags = torch.zeros((p, 16), dtype=torch.int64, device='cuda')
+    handles = []
+    for rank in range(p):
+        class FakeComm(object):
+            ranks = tuple(range(p))
+            _r = rank
+
+            def Get_size(self):
+                return p
+
+            def Get_rank(self):
+                return self._r
+        h = TransferHandle(FakeComm(), shape, 16, A[rank].shape, axisA, Bx[rank].shape, axisB, exchange=False)
+        h.set_flags([flags[j].data_ptr() for j in range(p)])
+        handles.append(h)
+    src = []
+    for r in range(p):
+        a = B.fftw.aligned(A[r].shape, dtype='D')
+        a[...] = A[r]
+        src.append(a)
+    dst = [B.fftw.aligned(d.shape, dtype='D', fill=0) for d in Bx]
+    ptrs = [device_ptr(d) for d in dst]
+    streams = [torch.cuda.Stream() for _ in range(p)]
+    torch.cuda.synchronize()
+    rounds = 5
+    for k in range(rounds):
+        for r in range(p):
+            with torch.cuda.stream(streams[r]):
+                handles[r].exchange_p2p(0, src[r], ptrs)          # barrier, put, barrier -- all flag kernels
+    torch.cuda.synchronize()
+    for r in range(p):
+        assert np.array_equal(np.asarray(dst[r]), Bx[r]), (p, r)
+    # every rank saw every peer arrive 2 * rounds times; nobody wrote its own slot
+    f = flags.cpu().numpy()
+    for j in range(p):
+        for i in range(p):
+            assert f[j, i] == (0 if i == j else 2 * rounds), (j, i, f)
+    for h in handles:
+        h.destroy()

@@ -86,6 +86,7 @@ def main():
             print("rot var %d  step %-17s %8.3f ms  %7.1f GB/s  %.3f" % (var, names[k], ms, gbs, gbs / peak), flush=True)
     _lib.set_option('rot_step_mask', 7)
     _lib.set_option('variant_rot', -1)
+    _lib.set_option('rotate', 0)
     # parity of the default against the classic schedule
     ref = B.fftw.aligned(shape, dtype=args.dtype)
     _lib.set_option('rotate', 0)
