@@ -324,11 +324,11 @@ _live_windows = None
 
 
 def _close_windows_at_exit():
-    """unmap peer windows and release the own ones while the CUDA context is still
-    alive (interpreter shutdown order is otherwise arbitrary)"""
+    """interpreter exit without PFFT.destroy(): unmap the peers' windows while the CUDA
+    context is still alive; the own windows are left to process teardown (see Window.release)"""
     for w in list(_live_windows or ()):
         try:
-            w.free()
+            w.release()
         except Exception:
             pass
 
@@ -354,8 +354,16 @@ class Window(object):
         self.tensor = torch.as_tensor(self._carrier, device=torch.device('cuda', torch.cuda.current_device()))
         assert self.tensor.data_ptr() == self.ptr
         self._peers = []
+        self._exported = False
+
+    def zero(self):
+        """clear the window and wait: peers may map (and poll) it right after"""
+        import torch
+        self.tensor.zero_()
+        torch.cuda.synchronize()
 
     def handle(self):
+        self._exported = True
         buf = C.create_string_buffer(64)
         check(lib().b2f_ipc_export(C.c_void_p(self.ptr), buf), 'b2f_ipc_export')
         return bytes(buf.raw)
@@ -377,14 +385,33 @@ class Window(object):
             self._peers = []
 
     def free(self):
+        """Release the window.  COLLECTIVE use only (PFFT.destroy): the caller has made sure
+        that no peer still maps or writes this memory (group barriers in _Buffers.free)."""
         if self.ptr:
             self.close_peers()
             self.tensor = None
             lib().b2f_free(C.c_void_p(self.ptr))
             self.ptr = 0
 
+    def release(self):
+        """Uncoordinated teardown (garbage collection, interpreter exit): a window that was
+        exported may still be mapped -- or being written -- by a peer, and freeing IPC-exported
+        memory under a peer is undefined behaviour.  So only the peers' windows are unmapped
+        here; the own allocation stays until the process (and with it every mapping) ends."""
+        if self.ptr:
+            self.close_peers()
+            if not self._exported:
+                self.tensor = None
+                lib().b2f_free(C.c_void_p(self.ptr))
+            else:
+                import warnings
+                warnings.warn("mpi4py_fft_b200: a peer-memory window was dropped without PFFT.destroy(); its %d MiB "
+                              "stay allocated until the process exits (destroy() is collective and frees them safely)"
+                              % (self.nbytes >> 20), ResourceWarning)
+            self.ptr = 0
+
     def __del__(self):
         try:
-            self.free()
+            self.release()
         except Exception:
             pass

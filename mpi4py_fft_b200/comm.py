@@ -127,6 +127,7 @@ class _World(object):
     def __init__(self):
         self._lock = threading.Lock()
         self._pg_cache = {}
+        self._pg_ident = None   # id of the default process group the cache belongs to
         self._virtual = None   # (size, rank) override for index-map tests
 
     # -- identity ----------------------------------------------------------
@@ -159,7 +160,16 @@ class _World(object):
             return None
         if len(ranks) == d.get_world_size():
             return d.group.WORLD
-        return self._pg_cache.get(tuple(ranks))
+        return self._cache(d).get(tuple(ranks))
+
+    def _cache(self, d):
+        """groups belong to ONE initialisation of the default process group: a cache left
+        over from a destroyed and re-initialised world would hand out dead groups"""
+        ident = id(d.group.WORLD)
+        if self._pg_ident != ident:
+            self._pg_cache = {}
+            self._pg_ident = ident
+        return self._pg_cache
 
     def make_groups(self, partitions):
         """Collectively create one group per partition (all world ranks call
@@ -167,11 +177,21 @@ class _World(object):
         d = self._dist()
         if d is None:
             return
+        cache = self._cache(d)
+        covered = sorted(r for part in partitions for r in part)
+        if covered != list(range(d.get_world_size())):
+            # torch.distributed.new_group is collective over the WORLD, not over the parent
+            # communicator (unlike MPI_Cart_sub): a grid on a strict subset of the ranks would
+            # leave the others out of the call and hang.  Fail loudly instead.
+            raise NotImplementedError(
+                "process grids must span every rank of the torch.distributed world (%d ranks); got partitions "
+                "covering ranks %s.  Build the Subcomm / PFFT on COMM_WORLD, or initialise torch.distributed "
+                "with the subset as its world." % (d.get_world_size(), covered[:16]))
         for part in partitions:
             part = tuple(part)
-            if part in self._pg_cache or len(part) == d.get_world_size():
+            if part in cache or len(part) == d.get_world_size():
                 continue
-            self._pg_cache[part] = d.new_group(ranks=list(part))
+            cache[part] = d.new_group(ranks=list(part))
 
 
 _world = _World()

@@ -329,11 +329,16 @@ int b2f_set_option(const char* key, int64_t value) {
     g_opts[key] = value;
     return B2F_OK;
 }
-int64_t b2f_get_option(const char* key) { return key ? option(key, 0) : 0; }
+int64_t b2f_get_option(const char* key) {
+    if (!key) return 0;
+    if (!strcmp(key, "sm_count")) return sm_count();   // device fact, read-only
+    return option(key, 0);
+}
 
 int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int64_t* sizes_out,
                   int naxes, const int* axes, const int* kind, int precision, unsigned flags) {
     (void)flags;
+    g_err.clear();   // the message reported with a failure is this call's, not an earlier one's
     if (!plan || !sizes_in || !sizes_out || !axes || !kind || ndims < 1 || naxes < 1 || naxes > ndims) {
         set_error("b2f_planxfftn: bad arguments");
         return B2F_EINVAL;

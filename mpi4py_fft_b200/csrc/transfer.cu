@@ -145,7 +145,7 @@ static cudaError_t launch_copy_blocks(const void* src, void* dst, long long oute
     const long long total = outer * n * U;
     if (total == 0) return cudaSuccess;
     long long blocks = (total + 255) / 256;
-    const long long cap = 148LL * 16;   // persistent-ish grid: 16 CTAs of 256 threads per SM
+    const long long cap = (long long)sm_count() * 16;   // persistent-ish grid: 16 CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     const BlockDist bd = make_dist(n, p);
     switch (v) {
@@ -158,35 +158,6 @@ static cudaError_t launch_copy_blocks(const void* src, void* dst, long long oute
     count_launch();
     return cudaGetLastError();
 }
-
-// ---- workspace: two grow-only staging buffers per device ------------------------
-struct Workspace {
-    void* buf[2] = {nullptr, nullptr};
-    size_t cap[2] = {0, 0};
-};
-static Workspace g_ws[64];
-static std::mutex g_ws_mu;
-static int workspace(int slot, size_t bytes, void** out) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    Workspace& w = g_ws[dev & 63];
-    if (w.cap[slot] < bytes) {
-        if (w.buf[slot]) {
-            e = cudaFree(w.buf[slot]);   // synchronises: no transfer in flight can still use it
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFree(workspace)");
-            w.buf[slot] = nullptr;
-            w.cap[slot] = 0;
-        }
-        e = cudaMalloc(&w.buf[slot], bytes);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(transfer workspace)");
-        w.cap[slot] = bytes;
-    }
-    *out = w.buf[slot];
-    return B2F_OK;
-}
-
 
 // ---- peer-memory put: the whole redistribution as ONE kernel ------------------
 // Every rank stores the block each peer needs straight into that peer's array
@@ -252,6 +223,10 @@ struct b2f_transfer_s {
     unsigned long long* flags[B2F_MAX_PEERS] = {};
     unsigned long long epoch = 0;
     bool has_flags = false;
+    // staging buffers of the pack -> NCCL -> unpack path: owned by the transfer (two transfers in
+    // flight on different streams must not share them), sized on first use, freed with the handle
+    void* ws[2] = {nullptr, nullptr};
+    size_t ws_cap[2] = {0, 0};
     int nranks, rank, ndims, itemsize;
     std::vector<long long> shape, subA, subB;
     int axisA, axisB;
@@ -360,7 +335,27 @@ int b2f_transfer_create(b2f_transfer* out, b2f_comm comm, int nranks, int rank, 
 }
 
 int b2f_transfer_destroy(b2f_transfer t) {
+    if (t) {
+        for (int k = 0; k < 2; ++k)
+            if (t->ws[k]) cudaFree(t->ws[k]);
+    }
     delete t;
+    return B2F_OK;
+}
+
+static int workspace(b2f_transfer t, int slot, size_t bytes, void** out) {
+    if (t->ws_cap[slot] < bytes) {
+        if (t->ws[slot]) {
+            cudaError_t e = cudaFree(t->ws[slot]);
+            t->ws[slot] = nullptr;
+            t->ws_cap[slot] = 0;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFree(transfer workspace)");
+        }
+        cudaError_t e = cudaMalloc(&t->ws[slot], bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(transfer workspace)");
+        t->ws_cap[slot] = bytes;
+    }
+    *out = t->ws[slot];
     return B2F_OK;
 }
 
@@ -425,13 +420,13 @@ static int run_transfer(b2f_transfer t, int direction, const void* d_src, void* 
     char* recvbase = (char*)d_dst;
     if (outerS != 1) {
         void* ws;
-        if ((rc = workspace(0, bytesS, &ws))) return rc;
+        if ((rc = workspace(t, 0, bytesS, &ws))) return rc;
         if ((rc = b2f_transfer_pack(t, direction, d_src, ws, st))) return rc;
         sendbase = (const char*)ws;
     }
     if (outerD != 1) {
         void* ws;
-        if ((rc = workspace(1, bytesD, &ws))) return rc;
+        if ((rc = workspace(t, 1, bytesD, &ws))) return rc;
         recvbase = (char*)ws;
     }
     const BlockDist dS = make_dist(NS, p), dD = make_dist(ND, p);
@@ -490,7 +485,8 @@ static cudaError_t launch_put(const PutParams& prm, cudaStream_t st) {
     for (int k = 0; k < prm.npeers; ++k) most = prm.peer[k].units > most ? prm.peer[k].units : most;
     if (most == 0) return cudaSuccess;
     long long blocks = (most + 4 * 256 - 1) / (4 * 256);
-    const long long cap = (long long)option("put_ctas_per_peer", (148LL * 8) / prm.npeers > 148 ? (148LL * 8) / prm.npeers : 148);
+    const long long nsm = sm_count();
+    const long long cap = (long long)option("put_ctas_per_peer", (nsm * 8) / prm.npeers > nsm ? (nsm * 8) / prm.npeers : nsm);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)prm.npeers);

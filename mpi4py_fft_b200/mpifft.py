@@ -63,10 +63,8 @@ class _Buffers(object):
                 self.windows[label] = w
                 handles[label] = w.handle()
             # arrival counters of the flag barrier: 16 x 8 bytes per transfer, zeroed before anybody maps them
-            import torch
             w = _lib.Window(_SYNC_SLOT * max(1, len(transfers)))
-            w.tensor.zero_()
-            torch.cuda.synchronize()
+            w.zero()
             self.windows[_SYNC] = w
             handles[_SYNC] = w.handle()
         except Exception as exc:   # e.g. IPC not permitted in this container
@@ -105,8 +103,16 @@ class _Buffers(object):
             agreed = all(comm.allgather(table is not None))
             self.peers[id(t)] = table if agreed else None
             if agreed and flag_barrier_enabled():
-                # group barrier = one small kernel on counters in peer memory instead of an NCCL all-reduce
-                t._plan().set_flags([ptr + ti * _SYNC_SLOT for ptr in table[_SYNC]])
+                # group barrier = one small kernel on counters in peer memory instead of an NCCL all-reduce;
+                # all ranks of the group use it or none does
+                handle = t._plan()
+                try:
+                    handle.set_flags([ptr + ti * _SYNC_SLOT for ptr in table[_SYNC]])
+                    mine = True
+                except Exception:
+                    mine = False
+                if not all(comm.allgather(mine)) and mine:
+                    handle.set_flags(None)
             if not agreed and me == 0:
                 import warnings
                 reasons = [e[1].get('error') for e in everyone if isinstance(e[1], dict) and e[1].get('error')]
@@ -312,8 +318,9 @@ class Transform(object):
         if key not in self._plan:
             ok = fused_enabled() and hasattr(st, 'can_scatter')
             if ok:
+                handle = tr._plan()       # collective (creates the group's communicator): never inside a try
                 try:
-                    ok = st.can_scatter(tr._plan(), direction)
+                    ok = st.can_scatter(handle, direction)
                 except Exception:
                     ok = False
             self._plan[key] = ok
@@ -374,21 +381,24 @@ class Transform(object):
             self._side = torch.cuda.Stream()
         side = self._side
         p = tr.comm.Get_size()
-        sms = pipeline_producer_sms(p)
+        nsm = sm_count()
+        sms = pipeline_producer_sms(p, nsm)
         handle = tr._plan()
+        # events are reused from call to call (one per chunk plus the join): no allocation on the hot path
+        evs = self._plan.get(('events', i))
+        if evs is None or len(evs) != len(chunks) + 1:
+            evs = self._plan[('events', i)] = [torch.cuda.Event() for _ in range(len(chunks) + 1)]
         for c, (pspec, cspec) in enumerate(chunks):
             flags = (1 if c == 0 else 0) | 2          # enter once, leave after every chunk
             prod.run_scatter_chunk(cur, normalize, handle, direction, peers, flags, pspec, grid_cap=sms)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            side.wait_event(ev)
+            evs[c].record(main)
+            side.wait_event(evs[c])
             with torch.cuda.stream(side):
                 # the last chunk has the GPU to itself; the others share it with the producer
                 last = c + 1 == len(chunks)
-                cons.run_chunk(recv, dst2, normalize, cspec, grid_cap=0 if last else max(8, 148 - sms))
-        done = torch.cuda.Event()
-        done.record(side)
-        main.wait_event(done)
+                cons.run_chunk(recv, dst2, normalize, cspec, grid_cap=0 if last else max(8, nsm - sms))
+        evs[-1].record(side)
+        main.wait_event(evs[-1])
 
     def _resolve(self, label, shape, dtype, src, out):
         if label == 'IN':
@@ -518,10 +528,22 @@ def pipeline_chunks(block_bytes=None):
             return 0
     if block_bytes is None or block_bytes < (64 << 20):
         return 0
+    if flag_barrier_enabled():
+        # a chunk barrier is one small kernel: at least 4 chunks even for small blocks (the tail of the
+        # consuming stage that nothing overlaps is 1/K of it); more than 8 did not pay on 2 or 4 GPUs
+        # (profiles/r2_pipeline.txt)
+        return int(max(4, min(8, block_bytes >> 30)))
     return int(max(2, min(16, block_bytes >> 30)))
 
 
-def pipeline_producer_sms(p):
+def sm_count():
+    """SMs of the current device, from the library (cudaDevAttrMultiProcessorCount)"""
+    from . import _lib
+    n = int(_lib.lib().b2f_get_option(b'sm_count'))
+    return n if n > 0 else 148
+
+
+def pipeline_producer_sms(p, nsm=148):
     """SMs given to the producing (NVLink-bound) stage of a pipelined redistribution
     in a group of p ranks; the consuming stage gets the rest.  The remote share
     (p-1)/p of the stage output crosses NVLink at about 1/8 of the HBM rate, so the
@@ -530,7 +552,7 @@ def pipeline_producer_sms(p):
     env = os.environ.get('B2F_PIPE_SMS')
     if env:
         return int(env)
-    return int(min(120, max(32, round(148 * 0.30 * p / (p - 1)))))
+    return int(min(0.8 * nsm, max(0.2 * nsm, round(nsm * 0.30 * p / (p - 1)))))
 
 
 def flag_barrier_enabled():
