@@ -311,6 +311,26 @@ class Clocks(object):
                 "power_w_max": float(max(power)), "samples": len(sm)}
 
 
+def gpu_local_cpus(torch, dev):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None"""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(','):
+            if '-' in part:
+                lo, hi = part.split('-')
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus if cpus and cpus != allowed else None
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------
 # closed-form input: a sum of plane waves
 # ---------------------------------------------------------------------------
@@ -565,9 +585,22 @@ def run_b200(args):
             if avail < need * 1.5:
                 raise MemoryError("host has %.0f GiB available, pinned staging needs %.0f GiB"
                                   % (avail / 2 ** 30, need / 2 ** 30))
-            h_in = pinned_empty(u.shape, fft.dtype(False))
-            h_out = pinned_empty(u.shape, fft.dtype(False))
-            h_in[...] = 0.5
+            # NUMA-local staging: pages are placed on the node of the allocating thread, so the rank
+            # allocates (and first touches) its pinned blocks while bound to the CPUs next to its GPU
+            # -- with 8 ranks on a two-socket host half the copies otherwise cross the socket link
+            before = os.sched_getaffinity(0)
+            local = gpu_local_cpus(torch, torch.cuda.current_device())
+            if local:
+                os.sched_setaffinity(0, local)
+            try:
+                h_in = pinned_empty(u.shape, fft.dtype(False))
+                h_out = pinned_empty(u.shape, fft.dtype(False))
+                h_in[...] = 0.5
+                h_out[...] = 0
+            finally:
+                os.sched_setaffinity(0, before)
+            numa_note = "allocated on the GPU's NUMA node (cpus %d..%d)" % (min(local), max(local)) if local else \
+                "single NUMA domain or no sysfs information"
         except Exception as exc:   # e.g. not enough host RAM for pinned staging buffers
             why = repr(exc)[:200]
             h_in = h_out = None
@@ -593,7 +626,7 @@ def run_b200(args):
             good = abs(h_out[(0,) * h_out.ndim] - 0.5) < (1e-12 if f64 else 1e-5)
             e2e = {"value": 2.0 * npts / dt / 1e9 if good else None, "unit": "GPoints/s",
                    "h2d_bytes_per_step": int(h_in.nbytes) * world, "d2h_bytes_per_step": int(h_out.nbytes) * world,
-                   "ms_per_step": dt * 1e3, "steps": e2e_steps, "host_memory": "pinned, one block per rank"}
+                   "ms_per_step": dt * 1e3, "steps": e2e_steps, "host_memory": "pinned, one block per rank; " + numa_note}
             if not good:
                 e2e["error"] = "round trip through host buffers did not reproduce the input"
         del h_in, h_out

@@ -118,6 +118,20 @@ B2F_API int b2f_pad_truncate(int mode, int half_spectrum, int precision,
                      int64_t outer, int64_t n_src, int64_t n_dst, int64_t inner,
                      double scale, void *stream);
 
+/*
+ * Fold that dealiasing step into the transform itself: after this call the SPECTRUM side of a
+ * one-axis plan (output of B2F_FORWARD / B2F_R2C, input of B2F_BACKWARD / B2F_C2R) is an
+ * (outer, n_keep, inner) block -- the forward kernel's last pass writes only the kept modes
+ * (Nyquist rule included), the backward kernel's first pass reads them and takes zeros for the
+ * rest, so the padded spectrum never exists in memory and the extra pass of b2f_pad_truncate
+ * goes.  sizes_in / sizes_out given at plan time stay the padded ones.  Returns
+ * B2F_EUNSUPPORTED when the plan's kernel family has no such flavour (c2c: lengths 3 * 2^k, the
+ * sizes a 3/2-rule solver pads to; r2c / c2r: every Stockham length); the caller then runs
+ * b2f_execute + b2f_pad_truncate.  n_keep = 0 switches it off.
+ * Replaces libfft.py:263-311 + 408-422 (truncate / pad, then scale) inside the FFT launch.
+ */
+B2F_API int b2f_plan_set_truncation(b2f_plan plan, int64_t n_keep);
+
 /* ---- (2) global transpose --------------------------------------------- */
 /* NCCL communicator for one 1-D process group (replaces the MPI
  * sub-communicator of MPI_Cart_sub, pencil.py:84-88).  The 128-byte id is

@@ -29,6 +29,7 @@ SYMBOLS = {
     'b2f_execute': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     'b2f_destroy_plan': (C.c_int, [C.c_void_p]),
     'b2f_plan_describe': (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    'b2f_plan_set_truncation': (C.c_int, [C.c_void_p, C.c_int64]),
     'b2f_pad_truncate': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_double, C.c_void_p]),
     'b2f_comm_unique_id': (C.c_int, [C.c_void_p]),
@@ -144,6 +145,11 @@ class Plan(object):
         check(lib().b2f_execute(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), float(scale),
                                 stream if stream is not None else current_stream_ptr()),
               'b2f_execute')
+
+    def set_truncation(self, n_keep):
+        """fold the dealiasing step into the transform (b2f_plan_set_truncation); False when this
+        plan's kernels have no such flavour"""
+        return lib().b2f_plan_set_truncation(self._h, int(n_keep)) == 0
 
     def can_scatter(self, transfer_handle, direction):
         """True when the stage's last pass can store into the owners' windows of

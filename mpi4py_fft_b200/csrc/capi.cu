@@ -248,6 +248,8 @@ struct b2f_plan_s {
     bool rot_swap = false;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // dealiasing folded into a one-axis stage (b2f_plan_set_truncation): modes kept on the spectrum side
+    long long trunc_keep = 0;
 };
 
 static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long long>& shp_in,
@@ -420,6 +422,34 @@ int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int6
     return B2F_OK;
 }
 
+int b2f_plan_set_truncation(b2f_plan pl, int64_t n_keep) {
+    if (!pl) return B2F_EINVAL;
+    if (n_keep == 0) {
+        pl->trunc_keep = 0;
+        return B2F_OK;
+    }
+    if (pl->steps.size() != 1) {
+        set_error("dealiasing can be folded into one-axis stages only");
+        return B2F_EUNSUPPORTED;
+    }
+    const Step& s = pl->steps[0];
+    const long long n = (s.kind == B2F_C2R) ? s.n_out : s.n_in;        // logical (padded) length
+    const long long full = (s.kind == B2F_R2C || s.kind == B2F_C2R) ? n / 2 + 1 : n;
+    if (n_keep < 1 || n_keep > full) {
+        set_error("b2f_plan_set_truncation: kept modes must be in [1, padded modes]");
+        return B2F_EINVAL;
+    }
+    const bool ok = (s.type == STEP_POW2 && is_mixed(n)) || s.type == STEP_REAL;
+    if (!ok) {
+        set_error("this stage's kernel family has no dealiasing flavour (c2c: lengths 3 * 2^k; r2c / c2r: every "
+                  "Stockham length); use b2f_pad_truncate");
+        return B2F_EUNSUPPORTED;
+    }
+    pl->trunc_keep = n_keep;
+    pl->rot.clear();
+    return B2F_OK;
+}
+
 int b2f_execute(b2f_plan pl, const void* d_in, void* d_out, double scale, void* stream) {
     if (!pl || !d_in || !d_out) {
         set_error("b2f_execute: null plan or buffer");
@@ -569,7 +599,19 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 prm.in_ostride = prm.out_ostride = s.n_in;
                 prm.npencils = s.outer;
             }
+            if (pl->trunc_keep > 0) {
+                // padded transform: the spectrum side (output of a forward, input of a backward
+                // transform) holds trunc_keep modes per pencil instead of n
+                prm.trunc.n = (int)pl->trunc_keep;
+                prm.trunc.np = n;
+                long long& side = s.swap ? prm.in_ostride : prm.out_ostride;
+                side = strided ? pl->trunc_keep * s.inner : pl->trunc_keep;
+            }
             const bool part = chunk && chunk->mode != 0;
+            if (part && pl->trunc_keep > 0) {
+                set_error("partial execution of a truncating stage is not supported");
+                return B2F_EUNSUPPORTED;
+            }
             if (part) {
                 const long long esz = 2LL * pl->precision;
                 long long off;
@@ -615,7 +657,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             //   strided_engine: 0 = auto, 1 = register path only, 2 = TMA only (sweeps)
             e = cudaErrorInvalidValue;
             bool done = false;
-            if (strided && engine != 1) {
+            if (strided && engine != 1 && pl->trunc_keep == 0) {
                 PeerStore peer_part;
                 const PeerStore* peer_arg = peer;
                 if (peer && part) {
@@ -666,6 +708,12 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 prm.in_ostride = mode == 1 ? nc : s.n_in;
                 prm.out_ostride = mode == 1 ? s.n_out : nc;
                 prm.npencils = s.outer;
+            }
+            if (pl->trunc_keep > 0) {
+                prm.trunc.n = (int)pl->trunc_keep;
+                prm.trunc.np = (int)nc + 1;
+                long long& side = mode == 1 ? prm.out_ostride : prm.in_ostride;
+                side = strided ? pl->trunc_keep * s.inner : pl->trunc_keep;
             }
             e = pl->precision == 8 ? launch_real_f64((int)nc, mode, strided, prm, s.outer, st)
                                    : launch_real_f32((int)nc, mode, strided, prm, s.outer, st);

@@ -285,6 +285,37 @@ struct PeerStore {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Dealiasing folded into a stage: a padded transform runs at length Np but its
+// SPECTRUM side is stored with only N modes (reference libfft.py:263-311,
+// FFTBase._truncation_forward / _padding_backward).  Full (c2c) spectrum:
+//   kept modes  k <= N/2            -> m = k
+//               k >= Np - N/2       -> m = k - (Np - N)
+//   for even N both halves meet at m = N/2: forward stores P[N/2] + P[Np - N/2],
+//   backward reads T[N/2] / 2 into both P[N/2] and P[Np - N/2].
+// Half (r2c) spectrum: kept k < N; for even N the last kept mode is made real and
+// doubled (forward) / halved (backward).  n == 0 switches the map off.
+// The forward kernel never writes a dropped mode and the backward kernel never
+// reads a zero: the separate truncation / zero-fill pass over the spectrum goes.
+// ---------------------------------------------------------------------------
+struct TruncMap {
+    int n;      // kept modes N (0: no truncation)
+    int np;     // modes of the padded spectrum Np (full: transform length; half: Np/2 + 1)
+    // full spectrum: index in the truncated array of padded mode k, or -1 (dropped);
+    // *partner is set when k is the upper copy of an even-N Nyquist mode
+    B2F_HD int full(int k, bool* partner) const {
+        *partner = false;
+        const int h = n / 2;
+        if (k <= h) return k;
+        if (k >= np - h) {
+            *partner = (n % 2 == 0) && (k == np - h);
+            return k - (np - n);
+        }
+        return -1;
+    }
+    B2F_HD bool even() const { return n % 2 == 0; }
+};
+
 // shared-memory index of point i of pencil p inside a CTA tile.
 //   CONTIG : pencils are separate rows, row pitch PITCH, one pad slot every
 //            2^PS points (keeps stride-R writes of pass 0 conflict free)
@@ -461,6 +492,72 @@ struct TileFFT {
             }
         }
     }
+    // ---- pass 0 load of a padded backward transform: the input holds tm.n modes ----
+    static B2F_HD void load_global_padded(C* v, int q, const C* __restrict__ gin, long long nstride, bool valid,
+                                          bool swap, const TruncMap& tm) {
+        constexpr int R = RAD::get(0);
+        constexpr int NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = q + b * TP + r * (N / R);
+                C a = {(T)0, (T)0};
+                bool partner;
+                const int m = tm.full(n, &partner);
+                if (valid && m >= 0) {
+                    a = gin[(long long)m * nstride];
+                    if (tm.even() && m == tm.n / 2) {
+                        a.x *= (T)0.5;
+                        a.y *= (T)0.5;
+                    }
+                }
+                if (swap) { T t = a.x; a.x = a.y; a.y = t; }
+                v[b * R + r] = a;
+            }
+        }
+    }
+    // ---- last pass store of a padded forward transform: only the kept modes are written;
+    //      nyq[p] carries P[Np - N/2] to the thread that stores m = N/2 (even N).
+    //      Phase A (before the barrier): publish the partner; phase B: store.
+    static B2F_HD void store_truncated_publish(const C* v, int p, int q, C* nyq, const TruncMap& tm, T scale) {
+        constexpr int R = RAD::get(NPASS - 1);
+        constexpr int NB = E / R;
+        if (!tm.even()) return;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = q + b * TP + r * (N / R);
+                if (n == tm.np - tm.n / 2) nyq[p] = {v[b * R + r].x * scale, v[b * R + r].y * scale};
+            }
+        }
+    }
+    static B2F_HD void store_truncated(const C* v, int p, int q, C* __restrict__ gout, long long nstride, bool valid,
+                                       bool swap, T scale, const C* nyq, const TruncMap& tm) {
+        constexpr int R = RAD::get(NPASS - 1);
+        constexpr int NB = E / R;
+        if (!valid) return;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int n = q + b * TP + r * (N / R);
+                bool partner;
+                const int m = tm.full(n, &partner);
+                if (m < 0 || partner) continue;
+                C a = v[b * R + r];
+                a.x *= scale;
+                a.y *= scale;
+                if (tm.even() && m == tm.n / 2) {
+                    a.x += nyq[p].x;
+                    a.y += nyq[p].y;
+                }
+                if (swap) { T t = a.x; a.x = a.y; a.y = t; }
+                gout[(long long)m * nstride] = a;
+            }
+        }
+    }
     // ---- last pass store into the owners' arrays (see PeerStore) ----------------
     static B2F_HD void store_peer(const C* v, int q, const PeerStore& ps, long long part, long long rest,
                                   bool valid, bool swap, T scale) {
@@ -490,8 +587,10 @@ struct TileFFT {
     //
     // r2c: with Z the transform of z (natural order in shared memory),
     //   X[k] = (Z[k] + conj Z[N-k])/2 - i w^k (Z[k] - conj Z[N-k])/2,   X[N] = Re Z[0] - Im Z[0]
+    // keep > 0: only the first `keep` modes of the half spectrum are stored (padded transform);
+    // for even keep the last one is made real and doubled (reference libfft.py:270-279)
     static B2F_HD void r2c_post(int p, int q, const C* smem, const C* __restrict__ w, C* __restrict__ gout,
-                                long long out_ns, bool valid, T scale) {
+                                long long out_ns, bool valid, T scale, int keep = 0) {
         if (!valid) return;
         const T h = (T)0.5 * scale;
 #pragma unroll
@@ -503,9 +602,14 @@ struct TileFFT {
             const C sm = a + b, d = a - b;
             const C t = cmul(w[k], d);
             C x = {(sm.x + t.y) * h, (sm.y - t.x) * h};
-            gout[(long long)k * out_ns] = x;
-            if (k == 0) {
+            if (keep > 0 && keep % 2 == 0 && k == keep - 1) {
+                x.x *= (T)2;
+                x.y = (T)0;
+            }
+            if (keep == 0 || k < keep) gout[(long long)k * out_ns] = x;
+            if (k == 0 && (keep == 0 || N < keep)) {
                 C xn = {(a.x - a.y) * scale, (T)0};
+                if (keep > 0 && keep % 2 == 0 && N == keep - 1) xn.x *= (T)2;
                 gout[(long long)N * out_ns] = xn;
             }
         }

@@ -32,6 +32,7 @@ struct FftParams {
     int swap;
     PeerStore peer;          // peer.p > 0: the last pass stores into the owners' arrays (fused redistribution)
     const void* rtw;         // real transforms: exp(-2 pi i k / 2N), k < N
+    TruncMap trunc;          // trunc.n > 0: the spectrum side holds only trunc.n modes (padded transform, fft_core.cuh)
 };
 
 #if defined(__CUDACC__)
@@ -54,7 +55,9 @@ struct MidPasses {
 // SWAP is a compile-time constant inside the body so that the re/im exchange
 // of the backward transform costs no register moves around the 16-byte
 // loads/stores (the kernel branches once on prm.swap).
-template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, bool SWAP, bool PEER>
+// TRUNC: dealiasing folded in (TruncMap): the forward transform (SWAP = false) stores only the
+// kept modes, the backward transform (SWAP = true) reads the kept modes and zeros for the rest.
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, bool SWAP, bool PEER, bool TRUNC = false>
 __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
     using C = cplx<T>;
@@ -94,7 +97,8 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
 
     C v[E];
-    TF::load_global(v, q, gin, in_ns, valid, SWAP);
+    if constexpr (TRUNC && SWAP) TF::load_global_padded(v, q, gin, in_ns, valid, SWAP, prm.trunc);
+    else TF::load_global(v, q, gin, in_ns, valid, SWAP);
     TF::template twiddle_dft<0>(v, q, tw);
     if constexpr (TF::NPASS > 1) {
         TF::template store_shared<0>(v, p, q, smem);
@@ -103,7 +107,13 @@ __device__ __forceinline__ void fft_pow2_body(const FftParams& prm) {
         TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
         TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
     }
-    if constexpr (PEER) {
+    if constexpr (TRUNC && !SWAP) {
+        // the upper copy of an even-N Nyquist mode travels through P extra slots behind the tile
+        C* nyq = smem + (TF::NPASS > 1 ? TF::SI::tile_elems : 0);
+        TF::store_truncated_publish(v, p, q, nyq, prm.trunc, (T)prm.scale);
+        __syncthreads();
+        TF::store_truncated(v, p, q, gout, out_ns, valid, SWAP, (T)prm.scale, nyq, prm.trunc);
+    } else if constexpr (PEER) {
         long long part = 0, rest = 0;
         if (valid) prm.peer.locate(po, pi, &part, &rest);
         TF::store_peer(v, q, prm.peer, part, rest, valid, SWAP, (T)prm.scale);
@@ -116,6 +126,18 @@ template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MIN
 __global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_kernel(const FftParams prm) {
     if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, false>(prm);
     else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false, false>(prm);
+}
+
+// dealiasing folded in: forward truncates on store, backward pads on load (optionally with the
+// fused redistribution store: the backward transform of a padded stage can scatter)
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_trunc_kernel(const FftParams prm) {
+    if (prm.swap) fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, false, true>(prm);
+    else fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, false, false, true>(prm);
+}
+template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
+__global__ void __launch_bounds__((N / E) * P, MINB) fft_pow2_trunc_peer_kernel(const FftParams prm) {
+    fft_pow2_body<T, N, E, RAD, P, STRIDED, PS, true, true, true>(prm);
 }
 
 // the same transform with the last pass storing into the owners' arrays (PeerStore)
@@ -181,17 +203,32 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
         }
     } else {
         // c2r: the half spectrum goes to shared memory first (X[N] in the extra slot)
+        // padded transform (keep > 0): the input holds only the first `keep` modes, the last of
+        // them real and halved when keep is even (reference libfft.py:289-298); the rest is zero
         const C* gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+        const int keep = prm.trunc.n;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = q + e * TF::TP;
             C a = {(T)0, (T)0};
-            if (valid) a = gin[(long long)k * in_ns];
+            if (valid && (keep == 0 || k < keep)) {
+                a = gin[(long long)k * in_ns];
+                if (keep > 0 && keep % 2 == 0 && k == keep - 1) {
+                    a.x *= (T)0.5;
+                    a.y = (T)0;
+                }
+            }
             smem[TF::SI::at(p, k)] = a;
         }
         if (q == 0) {
             C a = {(T)0, (T)0};
-            if (valid) a = gin[(long long)N * in_ns];
+            if (valid && (keep == 0 || N < keep)) {
+                a = gin[(long long)N * in_ns];
+                if (keep > 0 && keep % 2 == 0 && N == keep - 1) {
+                    a.x *= (T)0.5;
+                    a.y = (T)0;
+                }
+            }
             smem[TF::SI::tile_elems + p] = a;
         }
         __syncthreads();
@@ -216,7 +253,7 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
             for (int r = 0; r < RL; ++r) smem[TF::SI::at(p, q + b * TF::TP + r * (N / RL))] = v[b * RL + r];
         __syncthreads();
         C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
-        TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale);
+        TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
     } else {
         if (STRIDED) {
             if (valid) {

@@ -32,20 +32,37 @@ static const void* pass_twiddles() {
     return slot;
 }
 
+// translation units that define B2F_GROUP_TRUNC also build the dealiasing flavour of their
+// kernels (TruncMap): the 3 * 2^k lengths, which is what a 3/2-rule padded solver transforms
+#ifndef B2F_GROUP_TRUNC
+#define B2F_GROUP_TRUNC 0
+#endif
+
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB>
 static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStream_t st) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
     const bool peer = prm_in.peer.p > 0;
+    const bool trunc = prm_in.trunc.n > 0;
     auto kern = peer ? fft_pow2_peer_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>
                      : fft_pow2_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>;
-    constexpr size_t smem = TF::NPASS > 1 ? sizeof(cplx<T>) * (size_t)TF::SI::tile_elems : 0;
-    static bool attr_done[2] = {false, false};   // per instantiation and flavour
-    if (!attr_done[peer]) {
+    size_t smem = TF::NPASS > 1 ? sizeof(cplx<T>) * (size_t)TF::SI::tile_elems : 0;
+    if (trunc) {
+#if B2F_GROUP_TRUNC
+        if (peer && !prm_in.swap) return cudaErrorInvalidValue;   // a truncating store cannot scatter
+        kern = peer ? fft_pow2_trunc_peer_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>
+                    : fft_pow2_trunc_kernel<T, N, E, RAD, P, STRIDED, PS, MINB>;
+        smem += sizeof(cplx<T>) * (size_t)P;
+#else
+        return cudaErrorInvalidValue;
+#endif
+    }
+    static bool attr_done[4] = {false, false, false, false};   // per instantiation and flavour
+    if (!attr_done[peer + 2 * trunc]) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        attr_done[peer] = true;
+        attr_done[peer + 2 * trunc] = true;
     }
     FftParams prm = prm_in;
     prm.tw = pass_twiddles<T, RAD>();

@@ -158,6 +158,28 @@ class _PaddedStage(_Stage):
     def __init__(self, owner, planned, default_normalize, forward):
         _Stage.__init__(self, owner, planned, default_normalize)
         self._forward = forward
+        self._fused = None          # None: not tried yet; False: two-pass; else the truncating plan
+
+    def _fused_plan(self):
+        """the transform with the dealiasing step folded into its last (forward) or first
+        (backward) pass -- ``b2f_plan_set_truncation`` -- or False when the stage's kernels have
+        no such flavour (then: transform + ``b2f_pad_truncate``).  B2F_FUSED_PAD=0 disables."""
+        if self._fused is None:
+            import os
+            self._fused = False
+            if os.environ.get('B2F_FUSED_PAD', '1') not in ('0', 'false', 'no', ''):
+                from ._lib import Plan
+                pl = self._planned
+                own = self._owner
+                try:
+                    plan = Plan(pl.input_shape, pl.output_shape, pl.axes, pl.kinds, pl.precision)
+                    if plan.set_truncation(own.trunc_shape[own.axes[-1]]):
+                        self._fused = plan
+                    else:
+                        plan.destroy()
+                except Exception:
+                    self._fused = False
+        return self._fused
 
     @property
     def input_shape(self):
@@ -191,6 +213,12 @@ class _PaddedStage(_Stage):
         inner = int(np.prod(spec_shape[axis + 1:])) if axis + 1 < len(spec_shape) else 1
         n_pad, n_keep = spec_shape[axis], own.trunc_shape[axis]
         scale = own.M if normalize else 1.0
+        fused = self._fused_plan()
+        if fused:
+            # one launch: the padded spectrum never exists in memory
+            assert tuple(dst.shape) == tuple(self.output_shape) and tuple(src.shape) == tuple(self.input_shape)
+            fused.execute(device_ptr(src), device_ptr(dst), scale)
+            return dst
         Vp = own._array(own.fwd, 'out')                    # the padded spectrum, plan owned
         if self._forward:
             assert tuple(dst.shape) == own.trunc_shape
@@ -205,9 +233,14 @@ class _PaddedStage(_Stage):
         return dst
 
     def can_scatter(self, transfer_handle, direction):
-        # forward: the truncation pass comes last, nothing to fuse; backward: the
+        # forward: the truncating store comes last, it cannot scatter as well; backward: the
         # transform at the padded length is last and can store into the windows
-        return (not self._forward) and _Stage.can_scatter(self, transfer_handle, direction)
+        if self._forward:
+            return False
+        fused = self._fused_plan()
+        if fused:
+            return fused.can_scatter(transfer_handle, direction)
+        return _Stage.can_scatter(self, transfer_handle, direction)
 
     def run_scatter(self, src, work, normalize, transfer_handle, direction, peer_ptrs):
         from ._lib import pad_truncate
@@ -216,6 +249,12 @@ class _PaddedStage(_Stage):
         if normalize is None:
             normalize = self._default_normalize
         own = self._owner
+        fused = self._fused_plan()
+        if fused:
+            fused.execute_scatter(device_ptr(src), device_ptr(work) if work is not None else 0,
+                                  own.M if normalize else 1.0, transfer_handle, direction, peer_ptrs,
+                                  getattr(peer_ptrs, 'sync', True))
+            return
         axis = own.axes[-1]
         spec_shape = own.fwd.output_shape
         outer = int(np.prod(spec_shape[:axis])) if axis else 1
@@ -347,3 +386,8 @@ class FFT(FFTBase):
     def destroy(self):
         self.fwd.destroy()
         self.bck.destroy()
+        for st in (self.forward, self.backward):
+            pl = getattr(st, '_fused', None)
+            if pl:
+                pl.destroy()
+                st._fused = None

@@ -87,7 +87,8 @@ static int emu_one(const FftParams& prm_in, long long outer) {
         for (int tid = 0; tid < TF::THREADS; ++tid) {
             C* v = &regs[(size_t)tid * E];
             const int p = TF::pencil_of(tid), q = TF::slot_of(tid);
-            TF::load_global(v, q, loc[tid].gin, loc[tid].in_ns, loc[tid].valid, swap);
+            if (prm.trunc.n > 0 && swap) TF::load_global_padded(v, q, loc[tid].gin, loc[tid].in_ns, loc[tid].valid, swap, prm.trunc);
+            else TF::load_global(v, q, loc[tid].gin, loc[tid].in_ns, loc[tid].valid, swap);
             TF::template twiddle_dft<0>(v, q, tw);
             if (TF::NPASS > 1) TF::template store_shared<0>(v, p, q, smem.data());
         }
@@ -103,6 +104,19 @@ static int emu_one(const FftParams& prm_in, long long outer) {
         }
         // all loads of the CTA precede its stores (in-place safety is checked by
         // running in == out from the python side)
+        std::vector<C> nyq((size_t)P);
+        if (prm.trunc.n > 0 && !swap) {
+            // dealiasing flavour, forward: publish the Nyquist partner, barrier, truncated store
+            for (auto& z : nyq) { z.x = (T)1e30; z.y = (T)-1e30; }
+            for (int tid = 0; tid < TF::THREADS; ++tid)
+                TF::store_truncated_publish(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), nyq.data(), prm.trunc,
+                                            (T)prm.scale);
+            // __syncthreads()
+            for (int tid = 0; tid < TF::THREADS; ++tid)
+                TF::store_truncated(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), loc[tid].gout, loc[tid].out_ns,
+                                    loc[tid].valid, swap, (T)prm.scale, nyq.data(), prm.trunc);
+            continue;
+        }
         for (int tid = 0; tid < TF::THREADS; ++tid) {
             C* v = &regs[(size_t)tid * E];
             if (prm.peer.p > 0) {
@@ -378,15 +392,22 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
                 const C* gin = reinterpret_cast<const C*>(prm.in) + o * prm.in_ostride + i;
+                const int keep = prm.trunc.n;
                 for (int e = 0; e < E; ++e) {
                     const int k = q + e * TF::TP;
                     C a = {(T)0, (T)0};
-                    if (valid) a = gin[(long long)k * in_ns];
+                    if (valid && (keep == 0 || k < keep)) {
+                        a = gin[(long long)k * in_ns];
+                        if (keep > 0 && keep % 2 == 0 && k == keep - 1) { a.x *= (T)0.5; a.y = (T)0; }
+                    }
                     smem[TF::SI::at(p, k)] = a;
                 }
                 if (q == 0) {
                     C a = {(T)0, (T)0};
-                    if (valid) a = gin[(long long)N * in_ns];
+                    if (valid && (keep == 0 || N < keep)) {
+                        a = gin[(long long)N * in_ns];
+                        if (keep > 0 && keep % 2 == 0 && N == keep - 1) { a.x *= (T)0.5; a.y = (T)0; }
+                    }
                     smem[TF::SI::tile_elems + p] = a;
                 }
             }
@@ -421,7 +442,7 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
                 C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
-                TF::r2c_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale);
+                TF::r2c_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
             }
         } else {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
@@ -803,4 +824,54 @@ extern "C" int emu_rot_step(int precision, int n, int var, long long batches, lo
                             void* out, double scale, int swap) {
     EmuRotStep st{in, out, batches, I, O, O * n, n, I * O * n, (long long)n * I, I, I * O * n, scale, swap};
     return precision == 8 ? emu_rot_dispatch<double>(n, var, st) : emu_rot_dispatch<float>(n, var, st);
+}
+
+
+// ---- dealiasing folded into a stage (TruncMap, fft_core.cuh): (outer, n_pad, inner) physical side,
+// (outer, keep, inner) spectrum side.  kind: -1 forward c2c (truncating store), +1 backward c2c
+// (padding load), -2 r2c, +2 c2r; n = padded logical length.  Strides as capi.cu run_plan sets them.
+extern "C" int emu_fft_trunc(int precision, int kind, int n, int keep, long long outer, long long inner, const void* in,
+                             void* out, double scale) {
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.in = in;
+    prm.out = out;
+    prm.scale = scale;
+    const bool strided = inner > 1;
+    if (kind == -1 || kind == 1) {
+        prm.swap = kind == 1;
+        prm.trunc.n = keep;
+        prm.trunc.np = n;
+        if (strided) {
+            prm.in_ostride = prm.out_ostride = (long long)n * inner;
+            prm.in_nstride = prm.out_nstride = inner;
+            prm.inner = inner;
+            (prm.swap ? prm.in_ostride : prm.out_ostride) = (long long)keep * inner;
+        } else {
+            prm.in_ostride = prm.out_ostride = n;
+            prm.npencils = outer;
+            (prm.swap ? prm.in_ostride : prm.out_ostride) = keep;
+        }
+        if (precision == 8) return emu_dispatch<double>(n, 0, strided, prm, outer);
+        return emu_dispatch<float>(n, 0, strided, prm, outer);
+    }
+    const int mode = kind == -2 ? 1 : 2;
+    const int nc = n / 2;
+    const long long n_in = mode == 1 ? n : nc + 1, n_out = mode == 1 ? nc + 1 : n;
+    prm.trunc.n = keep;
+    prm.trunc.np = nc + 1;
+    if (strided) {
+        prm.in_ostride = n_in * inner;
+        prm.out_ostride = n_out * inner;
+        prm.in_nstride = prm.out_nstride = inner;
+        prm.inner = inner;
+        (mode == 1 ? prm.out_ostride : prm.in_ostride) = (long long)keep * inner;
+    } else {
+        prm.in_ostride = mode == 1 ? nc : n_in;
+        prm.out_ostride = mode == 1 ? n_out : nc;
+        prm.npencils = outer;
+        (mode == 1 ? prm.out_ostride : prm.in_ostride) = keep;
+    }
+    if (precision == 8) return emu_real_dispatch<double>(nc, mode, strided, prm, outer);
+    return emu_real_dispatch<float>(nc, mode, strided, prm, outer);
 }

@@ -689,3 +689,76 @@ def test_flag_barrier_kernel_index_logic(B, p):
             assert np.array_equal(np.asarray(dst[r]), Bx[r]), (p, r)
     for h in handles:
         h.destroy()
+
+
+@pytest.mark.parametrize('shape,axis,dtype', [((96, 40, 24), 0, 'D'), ((20, 96, 24), 1, 'D'), ((20, 30, 96), 2, 'D'),
+                                               ((20, 30, 96), 2, 'd'), ((40, 96, 6), 1, 'F'), ((12, 20, 192), 2, 'f'),
+                                               ((384, 10, 8), 0, 'D'), ((6, 10, 128), 2, 'd'), ((24, 95, 8), 1, 'D')])
+def test_dealiasing_folded_into_the_transform(B, shape, axis, dtype, monkeypatch):
+    """3/2-rule padded stages (lengths 3 * 2^k) run as ONE kernel: the forward transform's last pass
+    writes only the kept modes, the backward transform's first pass reads them
+    (b2f_plan_set_truncation) -- same values as the reference rule (libfft.py:263-311, restated in
+    oracle/pfft_oracle.py and pinned on the reference's fixtures) and as the two-pass form."""
+    import pfft_oracle as O
+    from mpi4py_fft_b200 import _lib
+    tol = 1e-12 if dtype in 'dD' else 1e-5
+    pf = 1.5
+    x = rand(shape, dtype, 31)
+    f = B.FFT(shape, axes=(axis,), dtype=dtype, padding=pf)
+    u = B.fftw.aligned(shape, dtype=dtype)
+    u[...] = x
+    n0 = _lib.launch_count()
+    got = np.asarray(f.forward(u)).copy()
+    launches = _lib.launch_count() - n0
+    n = shape[axis]
+    stockham = (n % 3 == 0 and (n // 3) & (n // 3 - 1) == 0) or (dtype in 'df' and n % 2 == 0 and (n // 2) & (n // 2 - 1) == 0)
+    fused = bool(f.forward._fused_plan())
+    assert fused == stockham, (shape, axis, dtype)
+    if fused:
+        assert launches == 1, launches
+    x64 = x.astype('D' if dtype in 'FD' else 'd')
+    ref = O.padded_stage_forward(x64, axis, pf)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    y = rand(ref.shape, ref.dtype, 32)
+    v = B.fftw.aligned(ref.shape, dtype=got.dtype)
+    v[...] = y
+    back = np.asarray(f.backward(v)).copy()
+    refb = O.padded_stage_backward(y.astype(got.dtype).astype(np.complex128), axis, n, dtype in 'df')
+    assert np.abs(back - refb).max() <= tol * max(1.0, np.abs(refb).max())
+    assert np.array_equal(np.asarray(v), y.astype(got.dtype))           # the truncated input survives
+    # two-pass form (transform + b2f_pad_truncate): same values
+    monkeypatch.setenv('B2F_FUSED_PAD', '0')
+    f2 = B.FFT(shape, axes=(axis,), dtype=dtype, padding=pf)
+    assert not f2.forward._fused_plan()
+    got2 = np.asarray(f2.forward(u))
+    assert np.abs(got2 - got).max() <= 10 * tol * max(1.0, np.abs(ref).max())
+    f.destroy()
+    f2.destroy()
+
+
+def test_padded_pfft_uses_fused_stages(B):
+    """PFFT(padding=1.5) on 64^3 -> 96^3: every stage is a padded 3 * 2^k stage, each one launch"""
+    import pfft_oracle as O
+    from mpi4py_fft_b200 import _lib
+    shape = (64, 64, 64)
+    fft = B.PFFT(B.COMM_WORLD, shape, dtype='D', padding=[1.5, 1.5, 1.5])
+    u = B.newDistArray(fft, False)
+    assert tuple(u.shape) == (96, 96, 96)
+    x = rand((96, 96, 96), 'D', 8)
+    u[...] = x
+    n0 = _lib.launch_count()
+    uh = fft.forward(u)
+    assert _lib.launch_count() - n0 == 3
+    ref = x
+    for ax in (2, 1, 0):
+        ref = O.padded_stage_forward(ref, ax, 1.5)
+    assert np.abs(np.asarray(uh) - ref).max() < 1e-12
+    n0 = _lib.launch_count()
+    ub = fft.backward(uh)
+    assert _lib.launch_count() - n0 == 3
+    refb = ref
+    for ax in (0, 1, 2):
+        refb = O.padded_stage_backward(refb, ax, 96, False)
+    assert np.abs(np.asarray(ub) - refb).max() < 1e-12
+    fft.destroy()
