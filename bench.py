@@ -55,6 +55,8 @@ def parse():
     ap.add_argument('--config', default=os.environ.get('B2F_BENCH_CASE', 'c3'))
     ap.add_argument('--size', type=int, default=int(os.environ.get('B2F_BENCH_SIZE', 0)),
                     help='cube edge of the c2c workload (overrides --config; debugging)')
+    ap.add_argument('--shape', default=os.environ.get('B2F_BENCH_SHAPE', ''),
+                    help='a,b,c[,d]: global shape instead of the configuration\'s (debugging a configuration at reduced size)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-size', type=int, default=int(os.environ.get('B2F_BENCH_CPU_SIZE', 0)),
                     help='cube edge of the cpu_baseline sample (0: the workload itself when the host has the memory)')
@@ -79,6 +81,14 @@ def workload(args, world):
         grid = {1: (1, 1), 2: (2, 1), 4: (2, 2)}.get(world, (world // 2, 2))
         return "4D c2c 256^4 complex128 grid %s forward+backward" % (tuple(grid),), (256,) * 4, 'D', dict(grid=grid)
     raise SystemExit("unknown --config %r" % c)
+
+
+def workload_with_overrides(args, world):
+    name, shape, dtype, kw = workload(args, world)
+    if args.shape:
+        shape = tuple(int(x) for x in args.shape.split(','))
+        name += " [REDUCED to %s]" % 'x'.join(str(x) for x in shape)
+    return name, shape, dtype, kw
 
 
 def metric_name(args):
@@ -230,7 +240,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     world = int(os.environ.get('WORLD_SIZE', args.gpus))
-    name, shape, dtype, kw = workload(args, max(world, args.gpus))
+    name, shape, dtype, kw = workload_with_overrides(args, max(world, args.gpus))
     shp = reference_shape(shape, dtype)
     reduced = tuple(shp) != tuple(shape)
     budget = float(os.environ.get('B2F_REF_BUDGET_S', 420))
@@ -414,7 +424,7 @@ def run_b200(args):
     world, rank = comm.Get_size(), comm.Get_rank()
     if world != args.gpus and rank == 0:
         print("note: --gpus %d but world size %d (launch with torchrun for N>1)" % (args.gpus, world), file=sys.stderr)
-    name, shape, dtype, kw = workload(args, world)
+    name, shape, dtype, kw = workload_with_overrides(args, world)
     real = dtype in 'fd'
     f64 = dtype in 'dD'
     npts = float(np.prod(shape))

@@ -224,8 +224,13 @@ static int staged_fallback(int n) {
 static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
 // 3 * 2^k, 3 <= n <= 6144: served by the radix-3/6/12/24 schedules
 static bool is_mixed(long long n) { return n >= 3 && n <= B2F_MIXED_MAX_N && n % 3 == 0 && (n == 3 || is_pow2(n / 3)); }
+// 5 * 2^k <= 1280 and 7 * 2^k <= 1792: the radix-5/10/20 and radix-7/14/28 schedules
+static bool is_mixed57(long long n) {
+    if (n >= 5 && n <= B2F_MIXED5_MAX_N && n % 5 == 0 && (n == 5 || is_pow2(n / 5))) return true;
+    return n >= 7 && n <= B2F_MIXED7_MAX_N && n % 7 == 0 && (n == 7 || is_pow2(n / 7));
+}
 // lengths with a Stockham kernel instance
-static bool is_stockham(long long n) { return (is_pow2(n) && n <= B2F_POW2_MAX_N) || is_mixed(n); }
+static bool is_stockham(long long n) { return (is_pow2(n) && n <= B2F_POW2_MAX_N) || is_mixed(n) || is_mixed57(n); }
 
 // does the chirp-z convolution of this transform fit the largest tile (M <= 8192)?
 static bool chirp_fits(int kind, long long n) {
@@ -643,6 +648,9 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 if (is_mixed(n))
                     return pl->precision == 8 ? launch_pow2_mixed_f64(n, v, strided, prm, outer, st)
                                               : launch_pow2_mixed_f32(n, v, strided, prm, outer, st);
+                if (is_mixed57(n))
+                    return pl->precision == 8 ? launch_pow2_mixed57_f64(n, v, strided, prm, outer, st)
+                                              : launch_pow2_mixed57_f32(n, v, strided, prm, outer, st);
                 if (pl->precision == 8) {
                     if (n <= 256) return launch_pow2_small_f64(n, v, strided, prm, outer, st);
                     if (n <= 1024) return launch_pow2_mid_f64(n, v, strided, prm, outer, st);

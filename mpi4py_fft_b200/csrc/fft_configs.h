@@ -120,6 +120,51 @@
     X(3072, 0, 24, 4, 30, 1, 6, 8, 8, 8)  \
     X(6144, 0, 24, 2, 30, 1, 24, 8, 8, 4)
 
+// lengths 5 * 2^k (<= 1280) and 7 * 2^k (<= 1792): radices {5, 10, 20} with 20 points per thread,
+// {7, 14, 28} with 28 points per thread, then radix-4 / radix-2 passes (every radix of a schedule
+// must divide E).  What FFTW plans for any N through its codelets
+// (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:49-76) these lengths get as Stockham kernels
+// instead of the chirp-z detour.
+#define B2F_CONTIG_MIXED57(X)             \
+    X(5, 0, 5, 128, 30, 1, 5)             \
+    X(10, 0, 10, 64, 30, 1, 10)           \
+    X(20, 0, 20, 64, 30, 1, 20)           \
+    X(40, 0, 20, 32, 3, 1, 20, 2)         \
+    X(80, 0, 20, 32, 3, 1, 20, 4)         \
+    X(160, 0, 20, 16, 3, 1, 20, 4, 2)     \
+    X(320, 0, 20, 8, 3, 1, 20, 4, 4)      \
+    X(640, 0, 20, 4, 3, 1, 20, 4, 4, 2)   \
+    X(1280, 0, 20, 2, 3, 1, 20, 4, 4, 4)  \
+    X(7, 0, 7, 128, 30, 1, 7)             \
+    X(14, 0, 14, 64, 30, 1, 14)           \
+    X(28, 0, 28, 32, 30, 1, 28)           \
+    X(56, 0, 28, 32, 3, 1, 28, 2)         \
+    X(112, 0, 28, 32, 3, 1, 28, 4)        \
+    X(224, 0, 28, 16, 3, 1, 28, 4, 2)     \
+    X(448, 0, 28, 8, 3, 1, 28, 4, 4)      \
+    X(896, 0, 28, 4, 3, 1, 28, 4, 4, 2)   \
+    X(1792, 0, 28, 2, 3, 1, 28, 4, 4, 4)
+
+#define B2F_STRIDED_MIXED57(X)            \
+    X(5, 0, 5, 128, 30, 1, 5)             \
+    X(10, 0, 10, 64, 30, 1, 10)           \
+    X(20, 0, 20, 64, 30, 1, 20)           \
+    X(40, 0, 20, 32, 30, 1, 20, 2)        \
+    X(80, 0, 20, 32, 30, 1, 20, 4)        \
+    X(160, 0, 20, 16, 30, 1, 20, 4, 2)    \
+    X(320, 0, 20, 8, 30, 1, 20, 4, 4)     \
+    X(640, 0, 20, 8, 30, 1, 20, 4, 4, 2)  \
+    X(1280, 0, 20, 8, 30, 1, 20, 4, 4, 4) \
+    X(7, 0, 7, 128, 30, 1, 7)             \
+    X(14, 0, 14, 64, 30, 1, 14)           \
+    X(28, 0, 28, 32, 30, 1, 28)           \
+    X(56, 0, 28, 32, 30, 1, 28, 2)        \
+    X(112, 0, 28, 32, 30, 1, 28, 4)       \
+    X(224, 0, 28, 16, 30, 1, 28, 4, 2)    \
+    X(448, 0, 28, 8, 30, 1, 28, 4, 4)     \
+    X(896, 0, 28, 8, 30, 1, 28, 4, 4, 2)  \
+    X(1792, 0, 28, 4, 30, 1, 28, 4, 4, 4)
+
 // TMA-staged strided kernels (fft_tma.cuh):
 //   X(N, VAR, E, P, PS, STAGES, SPLIT, MINB, radices...)
 //   STAGES  shared-memory stages the TMA engine fills ahead of the compute
@@ -293,10 +338,53 @@
     X(3072, 24, 4, 30, 1, 6, 8, 8, 8)    \
     X(6144, 24, 2, 30, 1, 24, 8, 8, 4)
 
-#define B2F_REAL_CONTIG(X) B2F_REAL_CONTIG_POW2(X) B2F_REAL_CONTIG_MIXED(X)
-#define B2F_REAL_STRIDED(X) B2F_REAL_STRIDED_POW2(X) B2F_REAL_STRIDED_MIXED(X)
-#define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X) B2F_CONTIG_MIXED(X)
-#define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X) B2F_STRIDED_MIXED(X)
+// real transforms of length 2N, N = 5 * 2^k or 7 * 2^k (rows of B2F_*_MIXED57 without the VAR column)
+#define B2F_REAL_CONTIG_MIXED57(X)       \
+    X(5, 5, 128, 30, 1, 5)               \
+    X(10, 10, 64, 30, 1, 10)             \
+    X(20, 20, 64, 30, 1, 20)             \
+    X(40, 20, 32, 3, 1, 20, 2)           \
+    X(80, 20, 32, 3, 1, 20, 4)           \
+    X(160, 20, 16, 3, 1, 20, 4, 2)       \
+    X(320, 20, 8, 3, 1, 20, 4, 4)        \
+    X(640, 20, 4, 3, 1, 20, 4, 4, 2)     \
+    X(1280, 20, 2, 3, 1, 20, 4, 4, 4)    \
+    X(7, 7, 128, 30, 1, 7)               \
+    X(14, 14, 64, 30, 1, 14)             \
+    X(28, 28, 32, 30, 1, 28)             \
+    X(56, 28, 32, 3, 1, 28, 2)           \
+    X(112, 28, 32, 3, 1, 28, 4)          \
+    X(224, 28, 16, 3, 1, 28, 4, 2)       \
+    X(448, 28, 8, 3, 1, 28, 4, 4)        \
+    X(896, 28, 4, 3, 1, 28, 4, 4, 2)     \
+    X(1792, 28, 2, 3, 1, 28, 4, 4, 4)
+
+#define B2F_REAL_STRIDED_MIXED57(X)      \
+    X(5, 5, 128, 30, 1, 5)               \
+    X(10, 10, 64, 30, 1, 10)             \
+    X(20, 20, 64, 30, 1, 20)             \
+    X(40, 20, 32, 30, 1, 20, 2)          \
+    X(80, 20, 32, 30, 1, 20, 4)          \
+    X(160, 20, 16, 30, 1, 20, 4, 2)      \
+    X(320, 20, 8, 30, 1, 20, 4, 4)       \
+    X(640, 20, 8, 30, 1, 20, 4, 4, 2)    \
+    X(1280, 20, 4, 30, 1, 20, 4, 4, 4)   \
+    X(7, 7, 128, 30, 1, 7)               \
+    X(14, 14, 64, 30, 1, 14)             \
+    X(28, 28, 32, 30, 1, 28)             \
+    X(56, 28, 32, 30, 1, 28, 2)          \
+    X(112, 28, 32, 30, 1, 28, 4)         \
+    X(224, 28, 16, 30, 1, 28, 4, 2)      \
+    X(448, 28, 8, 30, 1, 28, 4, 4)       \
+    X(896, 28, 8, 30, 1, 28, 4, 4, 2)    \
+    X(1792, 28, 4, 30, 1, 28, 4, 4, 4)
+
+#define B2F_REAL_CONTIG(X) B2F_REAL_CONTIG_POW2(X) B2F_REAL_CONTIG_MIXED(X) B2F_REAL_CONTIG_MIXED57(X)
+#define B2F_REAL_STRIDED(X) B2F_REAL_STRIDED_POW2(X) B2F_REAL_STRIDED_MIXED(X) B2F_REAL_STRIDED_MIXED57(X)
+#define B2F_CONTIG_ALL(X) B2F_CONTIG_SMALL(X) B2F_CONTIG_MID(X) B2F_CONTIG_LARGE(X) B2F_CONTIG_MIXED(X) B2F_CONTIG_MIXED57(X)
+#define B2F_STRIDED_ALL(X) B2F_STRIDED_SMALL(X) B2F_STRIDED_MID(X) B2F_STRIDED_LARGE(X) B2F_STRIDED_MIXED(X) B2F_STRIDED_MIXED57(X)
 
 #define B2F_POW2_MAX_N 8192
 #define B2F_MIXED_MAX_N 6144
+#define B2F_MIXED5_MAX_N 1280
+#define B2F_MIXED7_MAX_N 1792

@@ -89,6 +89,28 @@ B2F_HD cplx<T> mul_w24(cplx<T> a, int s) {
     return {a.x * c + a.y * sn, a.y * c - a.x * sn};
 }
 
+// multiply by W_40^s = exp(-2*pi*i*s/40), s a loop constant in [0,20): the butterfly
+// twiddles of the radices 10 and 20 (lengths 5 * 2^k)
+template <class T>
+B2F_HD cplx<T> mul_w40(cplx<T> a, int s) {
+    constexpr double C[20] = {1.0, 0.98768834059513777035, 0.95105651629515353118, 0.89100652418836789881, 0.80901699437494745126, 0.70710678118654757274, 0.58778525229247313710, 0.45399049973954680448, 0.30901699437494745126, 0.15643446504023092447, 0.00000000000000006123, -0.15643446504023059140, -0.30901699437494734024, -0.45399049973954669346, -0.58778525229247302608, -0.70710678118654746172, -0.80901699437494734024, -0.89100652418836778779, -0.95105651629515353118, -0.98768834059513765933};
+    constexpr double S[20] = {0.0, 0.15643446504023086896, 0.30901699437494739575, 0.45399049973954674897, 0.58778525229247313710, 0.70710678118654746172, 0.80901699437494745126, 0.89100652418836778779, 0.95105651629515353118, 0.98768834059513777035, 1.0, 0.98768834059513777035, 0.95105651629515364220, 0.89100652418836789881, 0.80901699437494745126, 0.70710678118654757274, 0.58778525229247324813, 0.45399049973954685999, 0.30901699437494750677, 0.15643446504023097998};
+    if (s == 0) return a;
+    if (s == 10) return mul_mi(a);
+    const T c = (T)C[s], sn = (T)S[s];
+    return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+}
+// multiply by W_56^s = exp(-2*pi*i*s/56), s in [0,28): radices 14 and 28 (lengths 7 * 2^k)
+template <class T>
+B2F_HD cplx<T> mul_w56(cplx<T> a, int s) {
+    constexpr double C[28] = {1.0, 0.99371220989324260398, 0.97492791218182361934, 0.94388333030836757409, 0.90096886790241914600, 0.84672419922828412453, 0.78183148246802980363, 0.70710678118654757274, 0.62348980185873359439, 0.53203207651533657163, 0.43388373911755817591, 0.33027906195516731902, 0.22252093395631444839, 0.11196447610330768907, 0.00000000000000006123, -0.11196447610330757805, -0.22252093395631433737, -0.33027906195516720800, -0.43388373911755806489, -0.53203207651533646061, -0.62348980185873348336, -0.70710678118654746172, -0.78183148246802947057, -0.84672419922828412453, -0.90096886790241903498, -0.94388333030836757409, -0.97492791218182373036, -0.99371220989324260398};
+    constexpr double S[28] = {0.0, 0.11196447610330785560, 0.22252093395631439288, 0.33027906195516709698, 0.43388373911755812040, 0.53203207651533657163, 0.62348980185873348336, 0.70710678118654746172, 0.78183148246802980363, 0.84672419922828412453, 0.90096886790241914600, 0.94388333030836746307, 0.97492791218182361934, 0.99371220989324260398, 1.0, 0.99371220989324260398, 0.97492791218182361934, 0.94388333030836746307, 0.90096886790241914600, 0.84672419922828423555, 0.78183148246802991466, 0.70710678118654757274, 0.62348980185873392745, 0.53203207651533668265, 0.43388373911755823142, 0.33027906195516720800, 0.22252093395631408757, 0.11196447610330798050};
+    if (s == 0) return a;
+    if (s == 14) return mul_mi(a);
+    const T c = (T)C[s], sn = (T)S[s];
+    return {a.x * c + a.y * sn, a.y * c - a.x * sn};
+}
+
 template <int R, class T>
 struct DftReg {
     static B2F_HD void run(cplx<T>* v) {
@@ -104,6 +126,8 @@ struct DftReg {
         for (int k = 0; k < R / 2; ++k) {
             cplx<T> t;
             if constexpr ((R & (R - 1)) == 0) t = mul_w32(o[k], k * (32 / R));
+            else if constexpr (R % 5 == 0) t = mul_w40(o[k], k * (40 / R));
+            else if constexpr (R % 7 == 0) t = mul_w56(o[k], k * (56 / R));
             else t = mul_w24(o[k], k * (24 / R));
             v[k] = e[k] + t;
             v[k + R / 2] = e[k] - t;
@@ -120,6 +144,49 @@ struct DftReg<3, T> {
         v[0] = v[0] + s;
         v[1] = m + r;
         v[2] = m - r;
+    }
+};
+// 5- and 7-point DFTs: the inputs pair up as v[k] +- v[R-k]; the sums see the cosines, the
+// differences the sines (forward sign: y[j] = m[j] - i s[j], y[R-j] = m[j] + i s[j])
+template <class T>
+struct DftReg<5, T> {
+    static B2F_HD void run(cplx<T>* v) {
+        const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;   // cos(2 pi / 5), cos(4 pi / 5)
+        const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;    // sin(2 pi / 5), sin(4 pi / 5)
+        const cplx<T> a1 = v[1] + v[4], a2 = v[2] + v[3], b1 = v[1] - v[4], b2 = v[2] - v[3];
+        const cplx<T> m1 = {v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y};
+        const cplx<T> m2 = {v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y};
+        const cplx<T> t1 = {s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y};
+        const cplx<T> t2 = {s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y};
+        v[0] = v[0] + a1 + a2;
+        v[1] = {m1.x + t1.y, m1.y - t1.x};   // m1 - i t1
+        v[4] = {m1.x - t1.y, m1.y + t1.x};
+        v[2] = {m2.x + t2.y, m2.y - t2.x};
+        v[3] = {m2.x - t2.y, m2.y + t2.x};
+    }
+};
+template <class T>
+struct DftReg<7, T> {
+    static B2F_HD void run(cplx<T>* v) {
+        const T c1 = (T)0.62348980185873353053, c2 = (T)-0.22252093395631440429, c3 = (T)-0.90096886790241912624;
+        const T s1 = (T)0.78183148246802980871, s2 = (T)0.97492791218182360702, s3 = (T)0.43388373911755812048;
+        const cplx<T> a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
+        const cplx<T> b1 = v[1] - v[6], b2 = v[2] - v[5], b3 = v[3] - v[4];
+        // cos(2 pi j k / 7): rows j = 1, 2, 3 over k = 1, 2, 3 are (c1 c2 c3), (c2 c3 c1), (c3 c1 c2);
+        // sin(2 pi j k / 7):                                      (s1 s2 s3), (s2 -s3 -s1), (s3 -s1 s2)
+        const cplx<T> m1 = {v[0].x + c1 * a1.x + c2 * a2.x + c3 * a3.x, v[0].y + c1 * a1.y + c2 * a2.y + c3 * a3.y};
+        const cplx<T> m2 = {v[0].x + c2 * a1.x + c3 * a2.x + c1 * a3.x, v[0].y + c2 * a1.y + c3 * a2.y + c1 * a3.y};
+        const cplx<T> m3 = {v[0].x + c3 * a1.x + c1 * a2.x + c2 * a3.x, v[0].y + c3 * a1.y + c1 * a2.y + c2 * a3.y};
+        const cplx<T> t1 = {s1 * b1.x + s2 * b2.x + s3 * b3.x, s1 * b1.y + s2 * b2.y + s3 * b3.y};
+        const cplx<T> t2 = {s2 * b1.x - s3 * b2.x - s1 * b3.x, s2 * b1.y - s3 * b2.y - s1 * b3.y};
+        const cplx<T> t3 = {s3 * b1.x - s1 * b2.x + s2 * b3.x, s3 * b1.y - s1 * b2.y + s2 * b3.y};
+        v[0] = v[0] + a1 + a2 + a3;
+        v[1] = {m1.x + t1.y, m1.y - t1.x};
+        v[6] = {m1.x - t1.y, m1.y + t1.x};
+        v[2] = {m2.x + t2.y, m2.y - t2.x};
+        v[5] = {m2.x - t2.y, m2.y + t2.x};
+        v[3] = {m3.x + t3.y, m3.y - t3.x};
+        v[4] = {m3.x - t3.y, m3.y + t3.x};
     }
 };
 template <class T>
@@ -413,7 +480,9 @@ struct TileFFT {
         constexpr int NB = E / R;
         static_assert(E % R == 0, "radix must divide E");
         static_assert(R <= 32, "radix above 32 is not implemented");
-        static_assert((R & (R - 1)) == 0 || R == 3 || R == 6 || R == 12 || R == 24, "radix must be 2^a or 3 * 2^a");
+        static_assert((R & (R - 1)) == 0 || R == 3 || R == 6 || R == 12 || R == 24 || R == 5 || R == 10 || R == 20 ||
+                          R == 7 || R == 14 || R == 28,
+                      "radix must be 2^a, 3 * 2^a, 5 * 2^a or 7 * 2^a");
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if (S > 0) {
@@ -502,16 +571,15 @@ struct TileFFT {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int n = q + b * TP + r * (N / R);
+                // the load itself is unconditional (a dropped mode re-reads mode 0, a cache hit) so
+                // that all E loads of the thread are in flight together; the value is selected after
                 C a = {(T)0, (T)0};
                 bool partner;
                 const int m = tm.full(n, &partner);
-                if (valid && m >= 0) {
-                    a = gin[(long long)m * nstride];
-                    if (tm.even() && m == tm.n / 2) {
-                        a.x *= (T)0.5;
-                        a.y *= (T)0.5;
-                    }
-                }
+                if (valid) a = gin[(long long)(m < 0 ? 0 : m) * nstride];
+                const T f = m < 0 ? (T)0 : (tm.even() && m == tm.n / 2) ? (T)0.5 : (T)1;
+                a.x *= f;
+                a.y *= f;
                 if (swap) { T t = a.x; a.x = a.y; a.y = t; }
                 v[b * R + r] = a;
             }

@@ -210,13 +210,15 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = q + e * TF::TP;
+            // unconditional load (a dropped mode re-reads mode 0), value selected afterwards: all E
+            // loads of the thread stay in flight together
+            const bool have = keep == 0 || k < keep;
             C a = {(T)0, (T)0};
-            if (valid && (keep == 0 || k < keep)) {
-                a = gin[(long long)k * in_ns];
-                if (keep > 0 && keep % 2 == 0 && k == keep - 1) {
-                    a.x *= (T)0.5;
-                    a.y = (T)0;
-                }
+            if (valid) a = gin[(long long)(have ? k : 0) * in_ns];
+            if (!have) a = {(T)0, (T)0};
+            if (keep > 0 && keep % 2 == 0 && k == keep - 1) {
+                a.x *= (T)0.5;
+                a.y = (T)0;
             }
             smem[TF::SI::at(p, k)] = a;
         }

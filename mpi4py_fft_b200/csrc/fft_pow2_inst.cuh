@@ -4,7 +4,9 @@
 // compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 #include "fft_pow2.cuh"
 #include "fft_configs.h"
@@ -85,12 +87,11 @@ static cudaError_t launch_one(const FftParams& prm_in, long long outer, cudaStre
 template <class T>
 static const void* real_twiddles(int N) {
     static std::mutex mu;
-    static const void* cache[64][16] = {};
-    int dev = 0, lg = 0;
+    static std::map<std::pair<int, int>, const void*> cache;   // (device, N): lengths of different families share a log2
+    int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    while ((1 << lg) < N) ++lg;
     std::lock_guard<std::mutex> lk(mu);
-    const void*& slot = cache[dev & 63][lg & 15];
+    const void*& slot = cache[std::make_pair(dev, N)];
     if (!slot) {
         std::vector<cplx<T>> h((size_t)N);
         build_real_twiddles<T>(h.data(), N);

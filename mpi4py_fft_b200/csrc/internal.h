@@ -25,6 +25,8 @@ cudaError_t launch_pow2_mid_f32  (int n, int var, bool strided, const FftParams&
 cudaError_t launch_pow2_large_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_pow2_mixed_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_pow2_mixed_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed57_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed57_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 
 // real transforms of even length 2n through the n-point schedule (fft_real_*.cu); mode 1 = r2c, 2 = c2r
 cudaError_t launch_real_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);

@@ -68,12 +68,13 @@ def test_docstring_vectors_on_device(B):
 
 
 @pytest.mark.parametrize('n', [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192,
-                               3, 6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144])
+                               3, 6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144,
+                               5, 10, 20, 40, 80, 160, 320, 640, 1280, 7, 14, 28, 56, 112, 224, 448, 896, 1792])
 @pytest.mark.parametrize('dt', ['D', 'F'])
 def test_stockham_pow2_c2c(B, n, dt):
     """contiguous axis, strided axes with ragged tiles, forward/backward, fused
-    normalisation, in place -- every variant of fft_configs.h; lengths 2^k and
-    3 * 2^k (radices 3, 6, 12, 24)"""
+    normalisation, in place -- every variant of fft_configs.h; lengths 2^k,
+    3 * 2^k (radices 3, 6, 12, 24), 5 * 2^k (5, 10, 20) and 7 * 2^k (7, 14, 28)"""
     from mpi4py_fft_b200 import _lib
     tol = TOL[dt.lower()]
     shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 2048 else [(2, n), (n, 5)]
@@ -103,7 +104,8 @@ def test_stockham_pow2_c2c(B, n, dt):
 
 
 @pytest.mark.parametrize('n', [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384,
-                               6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144, 12288])
+                               6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144, 12288,
+                               10, 20, 40, 80, 160, 320, 640, 1280, 2560, 14, 28, 56, 112, 224, 448, 896, 1792, 3584])
 @pytest.mark.parametrize('dt', ['d', 'f'])
 def test_stockham_real_transforms(B, n, dt):
     """r2c / c2r of even power-of-two length through the n/2-point Stockham kernel
@@ -299,7 +301,7 @@ def test_generic_lengths_c2c(B, n, dft_ref):
         p = B.fftw.fftn(U, axes=(axis,))
         y = np.asarray(p())
         assert relerr(y, np.fft.fft(z, axis=axis)) < 1e-12
-        expect = 'stockham' if n in (3, 6, 12, 24) else 'dense-matrix' if n <= 32 else 'chirpz'
+        expect = 'stockham' if n in (3, 5, 6, 7, 12, 24) else 'dense-matrix' if n <= 32 else 'chirpz'
         assert expect in p.plan().describe()
     z = rand((n,), 'D', 1)
     U = B.fftw.aligned((n,), dtype='D')

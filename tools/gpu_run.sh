@@ -51,8 +51,11 @@ launches)
     python tools/launch_summary.py gpurun_out/launches.csv | tail -20 ;;
 ncu)
     regex=$1; skip=$2; count=$3; out=$4; shift 4
-    ncu --set full --clock-control none --import-source on -k "regex:$regex" -s "$skip" -c "$count" -f -o "gpurun_out/$out" "$@" > "gpurun_out/$out.log" 2>&1
-    ls -la "gpurun_out/$out.ncu-rep" ;;
+    # the report stays on the box (gpurun brings back at most 64 MiB): what comes home is its summary
+    ncu --set full --clock-control none --import-source on -k "regex:$regex" -s "$skip" -c "$count" -f -o "/tmp/$out" "$@" > "gpurun_out/$out.log" 2>&1
+    python tools/ncu_summary.py "/tmp/$out.ncu-rep" > "gpurun_out/$out.txt" 2>&1
+    python tools/ncu_hot.py "/tmp/$out.ncu-rep" 24 >> "gpurun_out/$out.txt" 2>&1
+    grep -E "^==|time  |dram_rd|dram_wr|occupancy|stalls" "gpurun_out/$out.txt" | cut -c1-220 ;;
 probe)
     [ -x tools/probe/peer_probe.bin ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/probe/peer_probe.bin tools/probe/peer_probe.cu
     timeout 300 tools/probe/peer_probe.bin > gpurun_out/peer_probe.txt 2>&1
