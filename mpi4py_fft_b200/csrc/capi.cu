@@ -209,7 +209,11 @@ static int staged_default(int n, long long row_bytes) {
         default: return -1;
     }
 }
-static int staged_fallback(int n) {
+static int staged_fallback(int n, int precision) {
+    // n = 2048 complex64 (the C4 stages, rows at an odd 8-byte pitch): 32 points per thread and
+    // 512 threads keep the float kernel out of the 64-register cap that made var 100 spill
+    // (stage 1 of 2048^3 r2c: 30.1 -> 25.4 ms, profiles/r2_c4_variants.txt)
+    if (n == 2048 && precision == 4) return 102;
     switch (n) {
         case 384: return 101;
         case 768: return 100;
@@ -685,7 +689,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                     const long long row_bytes = s.inner * 2LL * pl->precision;
                     const int first = staged_default(n, row_bytes);
                     e = first >= 0 ? staged(first) : cudaErrorInvalidValue;
-                    if (e == cudaErrorInvalidValue && first >= 0 && first < 100) e = staged(staged_fallback(n));
+                    if (e == cudaErrorInvalidValue && first >= 0 && first < 100) e = staged(staged_fallback(n, pl->precision));
                 }
                 done = (e != cudaErrorInvalidValue) || engine == 2;
             }

@@ -240,7 +240,10 @@
     X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32) \
     X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8) \
     X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32) \
-    X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
+    X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8) \
+    X(2048, 1, 32, 4, 5, 1, 1, 17, 32, 8, 8) \
+    X(2048, 2, 32, 4, 5, 1, 1, 1, 32, 8, 8) \
+    X(2048, 3, 16, 2, 4, 1, 1, 17, 16, 16, 8)
 
 #define B2F_CPA_TABLE(X) B2F_CPA_TABLE_A(X) B2F_CPA_TABLE_B(X) B2F_CPA_TABLE_C(X)
 
