@@ -762,3 +762,34 @@ def test_padded_pfft_uses_fused_stages(B):
         refb = O.padded_stage_backward(refb, ax, 96, False)
     assert np.abs(np.asarray(ub) - refb).max() < 1e-12
     fft.destroy()
+
+
+def test_full_size_c3_closed_form_values(B):
+    """BASELINE.json config 3 on one GPU (3D c2c 1024^3 complex128): EVERY point of the forward
+    transform against a closed form -- the input is a sum of plane waves (bench.py plane_waves /
+    fill_plane_waves, phases reduced exactly in integers), whose normalised spectrum is a_m at k_m
+    and zero elsewhere -- then the round trip.  The same check runs inside bench.py at every N."""
+    import importlib.util
+    import os
+    import torch
+    from conftest import ROOT
+    from mpi4py_fft_b200.devarray import as_tensor
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2 ** 30:
+        pytest.skip("needs ~70 GiB of HBM")
+    spec = importlib.util.spec_from_file_location('b2f_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    shape = (1024, 1024, 1024)
+    fft = B.PFFT(B.COMM_WORLD, shape, dtype='D')
+    u = B.newDistArray(fft, False)
+    ks, amps = bench.plane_waves(shape, False)
+    bench.fill_plane_waves(torch, as_tensor(u), fft.local_slice(False), shape, False, ks, amps)
+    keep = as_tensor(u)[:4].clone()
+    uh = fft.forward(u)
+    back = B.newDistArray(fft, False)
+    fft.backward(uh, back)
+    err = bench.spectrum_error(torch, as_tensor(uh), fft.local_slice(True), ks, amps, False)
+    assert err < 1e-12, err
+    assert float((as_tensor(back)[:4] - keep).abs().max().item()) < 1e-12
+    assert float((as_tensor(back)[-4:] - as_tensor(u)[-4:]).abs().max().item()) < 1e-12
+    fft.destroy()
