@@ -290,6 +290,16 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
             set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
             return B2F_EINVAL;
         }
+    } else if ((kind == B2F_REDFT10 || kind == B2F_REDFT01 || kind == B2F_RODFT10 || kind == B2F_RODFT01) && n >= 4 &&
+               n % 2 == 0 && is_stockham(n / 2) && option("real_engine", 0) != 1 && option("r2r_engine", 0) != 1 &&
+               option("generic_engine", 0) == 0 && option("stockham", 1)) {
+        // DCT / DST of kinds II and III of even length: the n/2-point complex Stockham transform of the
+        // permuted (Makhoul) sequence plus a quarter-wave twiddle pass (fft_core.cuh r2r_*)
+        s.type = STEP_REAL;
+        if (s.n_out != s.n_in || in_c != 1 || out_c != 1) {
+            set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
+            return B2F_EINVAL;
+        }
     } else if (option("generic_engine", 0) != 1 && (n > option("dense_max", 32) || option("generic_engine", 0) == 2) &&
                chirp_fits(kind, n)) {
         // any other length / kind: chirp-z convolution on two power-of-two FFTs
@@ -448,7 +458,7 @@ int b2f_plan_set_truncation(b2f_plan pl, int64_t n_keep) {
         set_error("b2f_plan_set_truncation: kept modes must be in [1, padded modes]");
         return B2F_EINVAL;
     }
-    const bool ok = (s.type == STEP_POW2 && is_mixed(n)) || s.type == STEP_REAL;
+    const bool ok = (s.type == STEP_POW2 && is_mixed(n)) || (s.type == STEP_REAL && s.kind < B2F_REDFT00);
     if (!ok) {
         set_error("this stage's kernel family has no dealiasing flavour (c2c: lengths 3 * 2^k; r2c / c2r: every "
                   "Stockham length); use b2f_pad_truncate");
@@ -708,9 +718,16 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             prm.out = dst;
             prm.scale = sc;
             const bool strided = s.inner > 1;
-            const int mode = s.kind == B2F_R2C ? 1 : 2;
-            const long long nreal = mode == 1 ? s.n_in : s.n_out, nc = nreal / 2;
-            if (strided) {
+            const bool r2r = s.kind >= B2F_REDFT00;
+            const int mode = s.kind == B2F_R2C ? 1 : s.kind == B2F_C2R ? 2
+                           : (s.kind == B2F_REDFT10 || s.kind == B2F_RODFT10) ? 3 : 4;
+            const long long nreal = (mode == 2) ? s.n_out : s.n_in, nc = nreal / 2;
+            prm.flip = (s.kind == B2F_RODFT10 || s.kind == B2F_RODFT01) ? 1 : 0;
+            if (r2r && !strided) {
+                // real rows of n values on both sides
+                prm.in_ostride = prm.out_ostride = s.n_in;
+                prm.npencils = s.outer;
+            } else if (strided) {
                 prm.in_ostride = s.n_in * s.inner;
                 prm.out_ostride = s.n_out * s.inner;
                 prm.in_nstride = prm.out_nstride = s.inner;
@@ -721,7 +738,7 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 prm.out_ostride = mode == 1 ? s.n_out : nc;
                 prm.npencils = s.outer;
             }
-            if (pl->trunc_keep > 0) {
+            if (pl->trunc_keep > 0 && !r2r) {
                 prm.trunc.n = (int)pl->trunc_keep;
                 prm.trunc.np = (int)nc + 1;
                 long long& side = mode == 1 ? prm.out_ostride : prm.in_ostride;
@@ -798,7 +815,8 @@ int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
         char line[256];
         snprintf(line, sizeof(line), "%s kind=%d axis=%d n_in=%lld n_out=%lld outer=%lld inner=%lld %s->%s\n",
                  st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig")
-                 : st.type == STEP_REAL ? (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig")
+                 : st.type == STEP_REAL ? (st.kind >= B2F_REDFT00 ? (st.inner > 1 ? "stockham-r2r-strided" : "stockham-r2r-contig")
+                                                                   : (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig"))
                  : st.type == STEP_CHIRP ? (st.inner > 1 ? "chirpz-strided" : "chirpz-contig") : "dense-matrix",
                  st.kind, st.axis, st.n_in, st.n_out, st.outer, st.inner,
                  st.src == BUF_IN ? "in" : "out", st.dst == BUF_IN ? "in" : "out");

@@ -286,6 +286,18 @@ inline void build_real_twiddles(cplx<T>* out, int N) {
     }
 }
 
+// host: w4[k] = exp(-i pi k / (2 n)), n = 2N, k = 0..N: the quarter-wave twiddles of the
+// DCT / DST II and III through a real transform of the same length
+template <class T>
+inline void build_quarter_twiddles(cplx<T>* out, int N) {
+    const long double PI = 3.14159265358979323846264338327950288L;
+    for (int k = 0; k <= N; ++k) {
+        const long double a = PI * (long double)k / (long double)(4 * (long long)N);
+        out[k].x = (T)cosl(a);
+        out[k].y = (T)(-sinl(a));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Fused redistribution: the last pass of a stage can store straight into the
 // arrays of the ranks that own each part of the transformed axis (peer memory
@@ -707,6 +719,112 @@ struct TileFFT {
                 wc.y = -wc.y;
                 const C t = cmul(wc, d);
                 v[b * R + r] = {sm.y + t.x, sm.x - t.y};   // (re, im) = (sm.x - t.y, sm.y + t.x), swapped
+            }
+        }
+    }
+
+    // ---- r2r kinds II and III of even length n = 2N through the real transforms above
+    // (replaces fftw_plan_guru_r2r for FFTW_REDFT10 / REDFT01 / RODFT10 / RODFT01,
+    // /root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:69-75).  Makhoul's permutation
+    //     v[j] = x[2j],  v[n-1-j] = x[2j+1]                       (sigma below: v[j] = x[sigma(j)])
+    // turns the DCT-II into the real DFT V of v followed by a quarter-wave twiddle,
+    //     Y[k] = 2 Re(w4^k V[k]),  Y[n-k] = -2 Im(w4^k V[k]),   w4 = exp(-i pi / 2n),
+    // and the DCT-III into its transpose: V[k] = (X[k] - i X[n-k]) conj(w4^k) (X[n] = 0), v = c2r(V),
+    // y[sigma(j)] = v[j].  The sine kinds are the cosine kinds of the sign-alternated input with the
+    // output reversed (II), or of the reversed input with the output sign-alternated (III): `flip`.
+    static B2F_HD int r2r_sigma(int j) { return j < N ? 2 * j : 2 * (2 * N - 1 - j) + 1; }
+    static B2F_HD int r2r_pos(int k, bool flip) { return flip ? 2 * N - 1 - k : k; }
+    // kind II, pass-0 load: z[m] = v[2m] + i v[2m+1]
+    static B2F_HD void r2r_load(C* v, int q, const T* __restrict__ gin, long long ns, bool valid, bool flip) {
+        constexpr int R = RAD::get(0);
+        constexpr int NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int m = q + b * TP + r * (N / R);
+                const int i0 = r2r_sigma(2 * m), i1 = r2r_sigma(2 * m + 1);
+                C a = {(T)0, (T)0};
+                if (valid) {
+                    a.x = gin[(long long)i0 * ns];
+                    a.y = gin[(long long)i1 * ns];
+                }
+                if (flip) {
+                    if (i0 & 1) a.x = -a.x;
+                    if (i1 & 1) a.y = -a.y;
+                }
+                v[b * R + r] = a;
+            }
+        }
+    }
+    // kind II, after the N-point transform sits in shared memory in natural order: split as r2c_post,
+    // twiddle, store two reals per mode
+    static B2F_HD void r2r_post(int p, int q, const C* smem, const C* __restrict__ w, const C* __restrict__ w4,
+                                T* __restrict__ gout, long long out_ns, bool valid, T scale, bool flip) {
+        if (!valid) return;
+        const T h = (T)0.5 * scale;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = q + e * TP;
+            const C a = smem[SI::at(p, k)];
+            C b = smem[SI::at(p, k == 0 ? 0 : N - k)];
+            b.y = -b.y;
+            const C sm = a + b, d = a - b;
+            const C t = cmul(w[k], d);
+            const C x = {(sm.x + t.y) * h, (sm.y - t.x) * h};          // V[k] (scaled)
+            const C y = cmul(w4[k], x);
+            gout[(long long)r2r_pos(k, flip) * out_ns] = (T)2 * y.x;
+            if (k > 0) gout[(long long)r2r_pos(2 * N - k, flip) * out_ns] = (T)-2 * y.y;
+            if (k == 0) {
+                const T vn = (a.x - a.y) * scale;                       // V[N], real
+                gout[(long long)r2r_pos(N, flip) * out_ns] = (T)2 * w4[N].x * vn;
+            }
+        }
+    }
+    // kind III: the half spectrum V[k], k = 0..N, built from the real input straight into shared memory
+    // (where c2r_pre expects it: V[N] in the extra slot)
+    static B2F_HD void r2r_fill(int p, int q, C* smem, const C* __restrict__ w4, const T* __restrict__ gin,
+                                long long ns, bool valid, bool flip) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = q + e * TP;
+            C u = {(T)0, (T)0};
+            if (valid) {
+                u.x = gin[(long long)r2r_pos(k, flip) * ns];
+                u.y = k == 0 ? (T)0 : -gin[(long long)r2r_pos(2 * N - k, flip) * ns];
+            }
+            const C wc = {w4[k].x, -w4[k].y};
+            smem[SI::at(p, k)] = cmul(u, wc);
+        }
+        if (q == 0) {
+            C u = {(T)0, (T)0};
+            if (valid) {
+                u.x = gin[(long long)r2r_pos(N, flip) * ns];
+                u.y = -u.x;
+            }
+            const C wc = {w4[N].x, -w4[N].y};
+            smem[SI::tile_elems + p] = cmul(u, wc);
+        }
+    }
+    // kind III, last pass: (v.y, v.x) = (v[2m], v[2m+1]) of the c2r result -> y[sigma(j)] = v[j]
+    static B2F_HD void r2r_store(const C* v, int q, T* __restrict__ gout, long long out_ns, bool valid, T scale,
+                                 bool flip) {
+        constexpr int R = RAD::get(NPASS - 1);
+        constexpr int NB = E / R;
+        if (!valid) return;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int m = q + b * TP + r * (N / R);
+                const int i0 = r2r_sigma(2 * m), i1 = r2r_sigma(2 * m + 1);
+                T y0 = v[b * R + r].y * scale, y1 = v[b * R + r].x * scale;
+                if (flip) {
+                    if (i0 & 1) y0 = -y0;
+                    if (i1 & 1) y1 = -y1;
+                }
+                gout[(long long)i0 * out_ns] = y0;
+                gout[(long long)i1 * out_ns] = y1;
             }
         }
     }

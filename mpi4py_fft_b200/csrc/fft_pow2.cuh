@@ -33,6 +33,8 @@ struct FftParams {
     PeerStore peer;          // peer.p > 0: the last pass stores into the owners' arrays (fused redistribution)
     const void* rtw;         // real transforms: exp(-2 pi i k / 2N), k < N
     TruncMap trunc;          // trunc.n > 0: the spectrum side holds only trunc.n modes (padded transform, fft_core.cuh)
+    const void* qtw;         // r2r kinds II / III: exp(-i pi k / 4N), k <= N
+    int flip;                // r2r: sine kinds (RODFT10 / RODFT01)
 };
 
 #if defined(__CUDACC__)
@@ -180,8 +182,20 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
     const C* __restrict__ tw = reinterpret_cast<const C*>(prm.tw);
     const C* __restrict__ rtw = reinterpret_cast<const C*>(prm.rtw);
     const long long in_ns = STRIDED ? prm.in_nstride : 1, out_ns = STRIDED ? prm.out_nstride : 1;
+    const C* __restrict__ qtw = reinterpret_cast<const C*>(prm.qtw);
     C v[E];
-    if constexpr (MODE == 1) {
+    if constexpr (MODE == 3) {
+        // DCT-II / DST-II: real (outer, 2N, inner) in, permuted pairs
+        const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+        TF::r2r_load(v, q, gin, in_ns, valid, prm.flip != 0);
+    } else if constexpr (MODE == 4) {
+        // DCT-III / DST-III: the half spectrum is built from the real input in shared memory
+        const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+        TF::r2r_fill(p, q, smem, qtw, gin, in_ns, valid, prm.flip != 0);
+        __syncthreads();
+        TF::c2r_pre(v, p, q, smem, rtw);
+        __syncthreads();
+    } else if constexpr (MODE == 1) {
         constexpr int R0 = RAD::get(0);
         if (STRIDED) {
             const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
@@ -245,7 +259,10 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
         TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
         TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
     }
-    if constexpr (MODE == 1) {
+    if constexpr (MODE == 4) {
+        T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+        TF::r2r_store(v, q, gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
+    } else if constexpr (MODE == 1 || MODE == 3) {
         // Z in natural order -> shared memory -> split into the half spectrum
         if constexpr (TF::NPASS > 1) __syncthreads();   // the last pass has read the tile
         constexpr int RL = RAD::get(TF::NPASS - 1);
@@ -254,8 +271,13 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
 #pragma unroll
             for (int r = 0; r < RL; ++r) smem[TF::SI::at(p, q + b * TF::TP + r * (N / RL))] = v[b * RL + r];
         __syncthreads();
-        C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
-        TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
+        if constexpr (MODE == 3) {
+            T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+            TF::r2r_post(p, q, smem, rtw, qtw, gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
+        } else {
+            C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
+            TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
+        }
     } else {
         if (STRIDED) {
             if (valid) {

@@ -344,9 +344,10 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
     } else {
         grid = (prm.npencils + P - 1) / P;
     }
-    std::vector<C> twv((size_t)RAD::tw_total()), rtw((size_t)N);
+    std::vector<C> twv((size_t)RAD::tw_total()), rtw((size_t)N), qtw((size_t)N + 1);
     build_pass_twiddles<T, RAD>(twv.data());
     build_real_twiddles<T>(rtw.data(), N);
+    build_quarter_twiddles<T>(qtw.data(), N);
     const C* tw = twv.data();
     std::vector<C> smem((size_t)TF::SI::tile_elems + P);
     std::vector<C> regs((size_t)TF::THREADS * E);
@@ -367,7 +368,25 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
         };
         constexpr int R0 = RAD::get(0);
         constexpr int RL = RAD::get(TF::NPASS - 1);
-        if (MODE == 1) {
+        if (MODE == 3) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+                TF::r2r_load(&regs[(size_t)tid * E], TF::slot_of(tid), gin, in_ns, valid, prm.flip != 0);
+            }
+        } else if (MODE == 4) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+                TF::r2r_fill(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), qtw.data(), gin, in_ns, valid, prm.flip != 0);
+            }
+            // __syncthreads()
+            for (int tid = 0; tid < TF::THREADS; ++tid)
+                TF::c2r_pre(&regs[(size_t)tid * E], TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data());
+            // __syncthreads()
+        } else if (MODE == 1) {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 C* v = &regs[(size_t)tid * E];
                 const int q = TF::slot_of(tid);
@@ -429,7 +448,14 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
                 TF::template twiddle_dft<TF::NPASS - 1>(v, TF::slot_of(tid), tw);
             }
         }
-        if (MODE == 1) {
+        if (MODE == 4) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                TF::r2r_store(&regs[(size_t)tid * E], TF::slot_of(tid), gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
+            }
+        } else if (MODE == 1 || MODE == 3) {
             // __syncthreads()
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 const C* v = &regs[(size_t)tid * E];
@@ -441,8 +467,14 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
-                C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
-                TF::r2c_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
+                if (MODE == 3) {
+                    T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                    TF::r2r_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), qtw.data(), gout, out_ns, valid,
+                                 (T)prm.scale, prm.flip != 0);
+                } else {
+                    C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
+                    TF::r2c_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale, prm.trunc.n);
+                }
             }
         } else {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
@@ -470,10 +502,14 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
 
 #define EMU_REAL_CONTIG(N, E, P, PS, MINB, ...)                                                          \
     if (n == N) return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 1>(prm, outer) \
+                     : mode == 3 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 3>(prm, outer) \
+                     : mode == 4 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 4>(prm, outer) \
                                  : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 2>(prm, outer);
 #define EMU_REAL_STRIDED(N, E, P, PS, MINB, ...)                                                         \
     if (n == N)                                                                                          \
         return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 1>(prm, outer) \
+             : mode == 3 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 3>(prm, outer) \
+             : mode == 4 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 4>(prm, outer) \
                          : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 2>(prm, outer);
 
 template <class T>
@@ -874,4 +910,30 @@ extern "C" int emu_fft_trunc(int precision, int kind, int n, int keep, long long
     }
     if (precision == 8) return emu_real_dispatch<double>(nc, mode, strided, prm, outer);
     return emu_real_dispatch<float>(nc, mode, strided, prm, outer);
+}
+
+
+// ---- r2r kinds II / III through the real-transform kernels (fft_core.cuh r2r_*): (outer, n, inner) real in and out;
+// kind = FFTW integer 5 (REDFT10), 4 (REDFT01), 9 (RODFT10), 8 (RODFT01).  Strides as capi.cu run_plan sets them.
+extern "C" int emu_fft_r2r(int precision, int kind, int n, long long outer, long long inner, const void* in, void* out,
+                           double scale) {
+    if (n % 2 || (kind != 5 && kind != 4 && kind != 9 && kind != 8)) return -2;
+    FftParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.in = in;
+    prm.out = out;
+    prm.scale = scale;
+    prm.flip = (kind == 9 || kind == 8) ? 1 : 0;
+    const int mode = (kind == 5 || kind == 9) ? 3 : 4;
+    const bool strided = inner > 1;
+    if (strided) {
+        prm.in_ostride = prm.out_ostride = (long long)n * inner;
+        prm.in_nstride = prm.out_nstride = inner;
+        prm.inner = inner;
+    } else {
+        prm.in_ostride = prm.out_ostride = n;
+        prm.npencils = outer;
+    }
+    if (precision == 8) return emu_real_dispatch<double>(n / 2, mode, strided, prm, outer);
+    return emu_real_dispatch<float>(n / 2, mode, strided, prm, outer);
 }

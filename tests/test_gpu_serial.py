@@ -419,3 +419,44 @@ def test_errors(B):
     with pytest.raises(AssertionError):
         U = B.fftw.aligned((4, 4), dtype='d')
         B.fftw.fftn(U)
+
+
+@pytest.mark.parametrize('n', [4, 8, 64, 256, 1024, 4096, 96, 768, 160, 1280, 112, 896])
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_stockham_r2r_kinds_2_and_3(B, n, dt):
+    """DCT / DST of kinds II and III (FFTW_REDFT10 / REDFT01 / RODFT10 / RODFT01,
+    /root/reference/mpi4py_fft/fftw/xfftn.py:14-36) of even length as Stockham real transforms
+    (Makhoul permutation + n/2-point complex schedule + quarter-wave twiddle) against scipy:
+    contiguous and strided axes, ragged tiles, in place, inverse pairs, and the chirp-z kernels
+    (r2r_engine=1) as a second witness on the same input"""
+    from mpi4py_fft_b200 import _lib
+    fftw = B.fftw
+    tol = TOL[dt] * (10 if dt == 'f' else 1) * max(1.0, np.log2(n) / 4)
+    shapes = [(5, n), (3, n, 7), (n, 33)] if n <= 1024 else [(2, n), (n, 3)]
+    for shape in shapes:
+        axis = shape.index(n)
+        x = rand(shape, dt, seed=n + axis)
+        for typ in (2, 3):
+            for fam, planner, iplanner in (('dct', fftw.dctn, fftw.idctn), ('dst', fftw.dstn, fftw.idstn)):
+                A = fftw.aligned(shape, dtype=dt)
+                A[...] = x
+                p = planner(A, axes=(axis,), type=typ)
+                assert 'stockham-r2r' in p.plan().describe(), (n, fam, typ)
+                y = np.asarray(p()).copy()
+                ref = getattr(sfft, fam)(x.astype('d'), type=typ, axis=axis)
+                assert relerr(y, ref) < tol, (fam, typ, n, shape)
+                ip = iplanner(p.output_array, axes=(axis,), type=typ, output_array=A)
+                assert relerr(ip(normalize=True), x.astype('d')) < tol, ('inverse', fam, typ, n, shape)
+                # in place
+                A[...] = x
+                q = planner(A, axes=(axis,), type=typ, output_array=A)
+                assert relerr(q(), ref) < tol, ('in place', fam, typ, n, shape)
+                if n <= 1024 and shape is shapes[0]:
+                    _lib.set_option('r2r_engine', 1)
+                    try:
+                        A[...] = x
+                        c = planner(A, axes=(axis,), type=typ)
+                        assert 'stockham' not in c.plan().describe()
+                        assert relerr(c(), y) < tol
+                    finally:
+                        _lib.set_option('r2r_engine', 0)
