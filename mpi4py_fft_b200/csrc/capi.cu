@@ -290,11 +290,23 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
             set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
             return B2F_EINVAL;
         }
-    } else if ((kind == B2F_REDFT10 || kind == B2F_REDFT01 || kind == B2F_RODFT10 || kind == B2F_RODFT01) && n >= 4 &&
+    } else if ((kind == B2F_REDFT00 || kind == B2F_RODFT00) && is_stockham(kind == B2F_REDFT00 ? n - 1 : n + 1) &&
+               (kind == B2F_REDFT00 ? n - 1 : n + 1) >= 2 && option("real_engine", 0) != 1 && option("r2r_engine", 0) != 1 &&
+               option("generic_engine", 0) == 0 && option("stockham", 1)) {
+        // DCT-I of 2^k + 1 (Chebyshev grids) and DST-I of 2^k - 1 points (and the other Stockham families):
+        // the real transform of the even / odd extension of length 2(n -+ 1), read through an index map
+        s.type = STEP_REAL;
+        if (s.n_out != s.n_in || in_c != 1 || out_c != 1) {
+            set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
+            return B2F_EINVAL;
+        }
+    } else if ((kind == B2F_REDFT10 || kind == B2F_REDFT01 || kind == B2F_RODFT10 || kind == B2F_RODFT01 ||
+                kind == B2F_REDFT11 || kind == B2F_RODFT11) && n >= 4 &&
                n % 2 == 0 && is_stockham(n / 2) && option("real_engine", 0) != 1 && option("r2r_engine", 0) != 1 &&
                option("generic_engine", 0) == 0 && option("stockham", 1)) {
         // DCT / DST of kinds II and III of even length: the n/2-point complex Stockham transform of the
-        // permuted (Makhoul) sequence plus a quarter-wave twiddle pass (fft_core.cuh r2r_*)
+        // permuted (Makhoul) sequence plus a quarter-wave twiddle pass; kinds IV: the n/2-point transform of
+        // pre-twiddled pairs, post-twiddled (fft_core.cuh r2r_*, r2r4_*)
         s.type = STEP_REAL;
         if (s.n_out != s.n_in || in_c != 1 || out_c != 1) {
             set_error("sizes_in/sizes_out do not match the transform kind along axis " + std::to_string(axis));
@@ -720,9 +732,13 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
             const bool strided = s.inner > 1;
             const bool r2r = s.kind >= B2F_REDFT00;
             const int mode = s.kind == B2F_R2C ? 1 : s.kind == B2F_C2R ? 2
+                           : (s.kind == B2F_REDFT00 || s.kind == B2F_RODFT00) ? 5
+                           : (s.kind == B2F_REDFT11 || s.kind == B2F_RODFT11) ? 6
                            : (s.kind == B2F_REDFT10 || s.kind == B2F_RODFT10) ? 3 : 4;
-            const long long nreal = (mode == 2) ? s.n_out : s.n_in, nc = nreal / 2;
-            prm.flip = (s.kind == B2F_RODFT10 || s.kind == B2F_RODFT01) ? 1 : 0;
+            const long long nreal = (mode == 2) ? s.n_out : s.n_in;
+            // complex points of the schedule: half the real length; kinds I: half the extension's length
+            const long long nc = s.kind == B2F_REDFT00 ? s.n_in - 1 : s.kind == B2F_RODFT00 ? s.n_in + 1 : nreal / 2;
+            prm.flip = (s.kind == B2F_RODFT10 || s.kind == B2F_RODFT01 || s.kind == B2F_RODFT00 || s.kind == B2F_RODFT11) ? 1 : 0;
             if (r2r && !strided) {
                 // real rows of n values on both sides
                 prm.in_ostride = prm.out_ostride = s.n_in;

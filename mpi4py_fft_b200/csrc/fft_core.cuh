@@ -298,6 +298,21 @@ inline void build_quarter_twiddles(cplx<T>* out, int N) {
     }
 }
 
+// host: the two twiddle sets of the DCT / DST IV of length n = 2N through an N-point complex transform:
+// out[m] = exp(-i pi (4m + 1) / (4n)), m < N (input side), out[N + k] = exp(-i pi k / n), k < N (output side)
+template <class T>
+inline void build_dct4_twiddles(cplx<T>* out, int N) {
+    const long double PI = 3.14159265358979323846264338327950288L;
+    for (int m = 0; m < N; ++m) {
+        const long double a = PI * (long double)(4 * m + 1) / (long double)(8 * (long long)N);
+        out[m].x = (T)cosl(a);
+        out[m].y = (T)(-sinl(a));
+        const long double b = PI * (long double)m / (long double)(2 * (long long)N);
+        out[N + m].x = (T)cosl(b);
+        out[N + m].y = (T)(-sinl(b));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Fused redistribution: the last pass of a stage can store straight into the
 // arrays of the ranks that own each part of the transformed axis (peer memory
@@ -804,6 +819,92 @@ struct TileFFT {
             }
             const C wc = {w4[N].x, -w4[N].y};
             smem[SI::tile_elems + p] = cmul(u, wc);
+        }
+    }
+    // ---- r2r kinds I (FFTW_REDFT00 / RODFT00): the real DFT of the even / odd extension of length
+    // L = 2N.  DCT-I of n = N + 1 points: e[j] = X[j] (j <= N), e[L-j] = X[j];  Y[k] = Re E[k], k = 0..N.
+    // DST-I of n = N - 1 points: o[0] = o[N] = 0, o[j] = X[j-1], o[L-j] = -X[j-1];  Y[k-1] = -Im O[k], k = 1..N-1.
+    static B2F_HD T r2r1_elem(const T* __restrict__ gin, long long ns, int j, bool sine) {
+        if (!sine) return gin[(long long)(j <= N ? j : 2 * N - j) * ns];
+        if (j == 0 || j == N) return (T)0;
+        return j < N ? gin[(long long)(j - 1) * ns] : -gin[(long long)(2 * N - j - 1) * ns];
+    }
+    static B2F_HD void r2r1_load(C* v, int q, const T* __restrict__ gin, long long ns, bool valid, bool sine) {
+        constexpr int R = RAD::get(0);
+        constexpr int NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int m = q + b * TP + r * (N / R);
+                C a = {(T)0, (T)0};
+                if (valid) {
+                    a.x = r2r1_elem(gin, ns, 2 * m, sine);
+                    a.y = r2r1_elem(gin, ns, 2 * m + 1, sine);
+                }
+                v[b * R + r] = a;
+            }
+        }
+    }
+    static B2F_HD void r2r1_post(int p, int q, const C* smem, const C* __restrict__ w, T* __restrict__ gout,
+                                 long long out_ns, bool valid, T scale, bool sine) {
+        if (!valid) return;
+        const T h = (T)0.5 * scale;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = q + e * TP;
+            const C a = smem[SI::at(p, k)];
+            C b = smem[SI::at(p, k == 0 ? 0 : N - k)];
+            b.y = -b.y;
+            const C sm = a + b, d = a - b;
+            const C t = cmul(w[k], d);
+            const C x = {(sm.x + t.y) * h, (sm.y - t.x) * h};          // spectrum of the extension at k (scaled)
+            if (!sine) {
+                gout[(long long)k * out_ns] = x.x;
+                if (k == 0) gout[(long long)N * out_ns] = (a.x - a.y) * scale;
+            } else if (k > 0) {
+                gout[(long long)(k - 1) * out_ns] = -x.y;
+            }
+        }
+    }
+    // ---- r2r kinds IV (FFTW_REDFT11 / RODFT11) of even length n = 2N: ONE N-point complex transform,
+    //   c[m] = (x[2m] + i x[n-1-2m]) exp(-i pi (4m+1) / 4n),  C = FFT_N(c),  d[k] = C[k] exp(-i pi k / n),
+    //   Y[2k] = 2 Re d[k],  Y[n-1-2k] = -2 Im d[k];   the sine kind reverses the input and alternates the
+    //   sign of the output.  t4 = build_dct4_twiddles.
+    static B2F_HD void r2r4_load(C* v, int q, const T* __restrict__ gin, long long ns, bool valid, bool sine,
+                                 const C* __restrict__ t4) {
+        constexpr int R = RAD::get(0);
+        constexpr int NB = E / R;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int m = q + b * TP + r * (N / R);
+                C a = {(T)0, (T)0};
+                if (valid) {
+                    const T lo = gin[(long long)(2 * m) * ns], hi = gin[(long long)(2 * N - 1 - 2 * m) * ns];
+                    a.x = sine ? hi : lo;
+                    a.y = sine ? lo : hi;
+                }
+                v[b * R + r] = cmul(a, t4[m]);
+            }
+        }
+    }
+    static B2F_HD void r2r4_store(const C* v, int q, T* __restrict__ gout, long long out_ns, bool valid, T scale,
+                                  bool sine, const C* __restrict__ t4) {
+        constexpr int R = RAD::get(NPASS - 1);
+        constexpr int NB = E / R;
+        if (!valid) return;
+        const T s2 = (T)2 * scale;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k = q + b * TP + r * (N / R);
+                const C d = cmul(v[b * R + r], t4[N + k]);
+                gout[(long long)(2 * k) * out_ns] = s2 * d.x;
+                gout[(long long)(2 * N - 1 - 2 * k) * out_ns] = sine ? s2 * d.y : -s2 * d.y;
+            }
         }
     }
     // kind III, last pass: (v.y, v.x) = (v[2m], v[2m+1]) of the c2r result -> y[sigma(j)] = v[j]

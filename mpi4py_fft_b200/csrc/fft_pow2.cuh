@@ -184,7 +184,15 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
     const long long in_ns = STRIDED ? prm.in_nstride : 1, out_ns = STRIDED ? prm.out_nstride : 1;
     const C* __restrict__ qtw = reinterpret_cast<const C*>(prm.qtw);
     C v[E];
-    if constexpr (MODE == 3) {
+    if constexpr (MODE == 6) {
+        // DCT-IV / DST-IV: pre-twiddled pairs (x[2m], x[n-1-2m]), no real-transform split afterwards
+        const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+        TF::r2r4_load(v, q, gin, in_ns, valid, prm.flip != 0, qtw);
+    } else if constexpr (MODE == 5) {
+        // DCT-I / DST-I: even / odd extension of the n = N + 1 (N - 1) input points, read through an index map
+        const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+        TF::r2r1_load(v, q, gin, in_ns, valid, prm.flip != 0);
+    } else if constexpr (MODE == 3) {
         // DCT-II / DST-II: real (outer, 2N, inner) in, permuted pairs
         const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
         TF::r2r_load(v, q, gin, in_ns, valid, prm.flip != 0);
@@ -259,10 +267,16 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
         TF::template load_shared<TF::NPASS - 1>(v, p, q, smem);
         TF::template twiddle_dft<TF::NPASS - 1>(v, q, tw);
     }
-    if constexpr (MODE == 4) {
+    if constexpr (MODE == 6) {
+        // in place: every thread of the tile must have read its inputs before anybody stores -- with one
+        // pass nothing else separates the two
+        if constexpr (TF::NPASS == 1) __syncthreads();
+        T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+        TF::r2r4_store(v, q, gout, out_ns, valid, (T)prm.scale, prm.flip != 0, qtw);
+    } else if constexpr (MODE == 4) {
         T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
         TF::r2r_store(v, q, gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
-    } else if constexpr (MODE == 1 || MODE == 3) {
+    } else if constexpr (MODE == 1 || MODE == 3 || MODE == 5) {
         // Z in natural order -> shared memory -> split into the half spectrum
         if constexpr (TF::NPASS > 1) __syncthreads();   // the last pass has read the tile
         constexpr int RL = RAD::get(TF::NPASS - 1);
@@ -274,6 +288,9 @@ __device__ __forceinline__ void fft_real_body(const FftParams& prm) {
         if constexpr (MODE == 3) {
             T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
             TF::r2r_post(p, q, smem, rtw, qtw, gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
+        } else if constexpr (MODE == 5) {
+            T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+            TF::r2r1_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
         } else {
             C* gout = reinterpret_cast<C*>(prm.out) + o * prm.out_ostride + i;
             TF::r2c_post(p, q, smem, rtw, gout, out_ns, valid, (T)prm.scale, prm.trunc.n);

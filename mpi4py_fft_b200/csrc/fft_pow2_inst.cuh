@@ -123,6 +123,26 @@ static const void* quarter_twiddles(int N) {
     return slot;
 }
 
+// input- and output-side twiddles of the r2r kinds IV (build_dct4_twiddles), one table per (T, N) and device
+template <class T>
+static const void* dct4_twiddles(int N) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, const void*> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    const void*& slot = cache[std::make_pair(dev, N)];
+    if (!slot) {
+        std::vector<cplx<T>> h((size_t)2 * N);
+        build_dct4_twiddles<T>(h.data(), N);
+        void* d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(cplx<T>)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, h.data(), h.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        slot = d;
+    }
+    return slot;
+}
+
 template <class T, int N, int E, class RAD, int P, bool STRIDED, int PS, int MINB, int MODE>
 static cudaError_t launch_real_one(const FftParams& prm_in, long long outer, cudaStream_t st) {
     using TF = TileFFT<T, N, E, RAD, P, STRIDED, PS>;
@@ -140,8 +160,12 @@ static cudaError_t launch_real_one(const FftParams& prm_in, long long outer, cud
     prm.tw = pass_twiddles<T, RAD>();
     prm.rtw = real_twiddles<T>(N);
     if (!prm.tw || !prm.rtw) return cudaErrorMemoryAllocation;
-    if (MODE >= 3) {
+    if (MODE == 3 || MODE == 4) {
         prm.qtw = quarter_twiddles<T>(N);
+        if (!prm.qtw) return cudaErrorMemoryAllocation;
+    }
+    if (MODE == 6) {
+        prm.qtw = dct4_twiddles<T>(N);
         if (!prm.qtw) return cudaErrorMemoryAllocation;
     }
     long long grid;
@@ -158,12 +182,14 @@ static cudaError_t launch_real_one(const FftParams& prm_in, long long outer, cud
     return cudaGetLastError();
 }
 
-// mode 1 = r2c, 2 = c2r, 3 = r2r kinds II (REDFT10 / RODFT10), 4 = r2r kinds III (REDFT01 / RODFT01)
+// mode 1 = r2c, 2 = c2r, 3 = r2r kinds II (REDFT10 / RODFT10), 4 = kinds III (REDFT01 / RODFT01), 5 = kinds I (REDFT00 / RODFT00), 6 = kinds IV (REDFT11 / RODFT11)
 #define B2F_INST_REAL_CONTIG(N, E, P, PS, MINB, ...)                                                       \
     if (n == N) {                                                                                          \
         if (mode == 1) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 1>(prm, outer, st); \
         if (mode == 3) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 3>(prm, outer, st); \
         if (mode == 4) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 4>(prm, outer, st); \
+        if (mode == 5) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 5>(prm, outer, st); \
+        if (mode == 6) return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 6>(prm, outer, st); \
         return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, MINB, 2>(prm, outer, st);      \
     }
 #define B2F_INST_REAL_STRIDED(N, E, P, PS, MINB, ...)                                                      \
@@ -174,6 +200,10 @@ static cudaError_t launch_real_one(const FftParams& prm_in, long long outer, cud
             return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 3>(prm, outer, st); \
         if (mode == 4)                                                                                     \
             return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 4>(prm, outer, st); \
+        if (mode == 5)                                                                                     \
+            return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 5>(prm, outer, st); \
+        if (mode == 6)                                                                                     \
+            return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 6>(prm, outer, st); \
         return launch_real_one<T, N, E, Radices<__VA_ARGS__>, P * StridedScale<T>::value, true, PS, MINB, 2>(prm, outer, st);     \
     }
 

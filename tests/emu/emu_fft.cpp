@@ -348,6 +348,8 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
     build_pass_twiddles<T, RAD>(twv.data());
     build_real_twiddles<T>(rtw.data(), N);
     build_quarter_twiddles<T>(qtw.data(), N);
+    std::vector<C> t4((size_t)2 * N);
+    build_dct4_twiddles<T>(t4.data(), N);
     const C* tw = twv.data();
     std::vector<C> smem((size_t)TF::SI::tile_elems + P);
     std::vector<C> regs((size_t)TF::THREADS * E);
@@ -368,7 +370,21 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
         };
         constexpr int R0 = RAD::get(0);
         constexpr int RL = RAD::get(TF::NPASS - 1);
-        if (MODE == 3) {
+        if (MODE == 6) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+                TF::r2r4_load(&regs[(size_t)tid * E], TF::slot_of(tid), gin, in_ns, valid, prm.flip != 0, t4.data());
+            }
+        } else if (MODE == 5) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                const T* gin = reinterpret_cast<const T*>(prm.in) + o * prm.in_ostride + i;
+                TF::r2r1_load(&regs[(size_t)tid * E], TF::slot_of(tid), gin, in_ns, valid, prm.flip != 0);
+            }
+        } else if (MODE == 3) {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
@@ -448,14 +464,21 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
                 TF::template twiddle_dft<TF::NPASS - 1>(v, TF::slot_of(tid), tw);
             }
         }
-        if (MODE == 4) {
+        if (MODE == 6) {
+            for (int tid = 0; tid < TF::THREADS; ++tid) {
+                long long o, i; bool valid;
+                coords(tid, o, i, valid);
+                T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                TF::r2r4_store(&regs[(size_t)tid * E], TF::slot_of(tid), gout, out_ns, valid, (T)prm.scale, prm.flip != 0, t4.data());
+            }
+        } else if (MODE == 4) {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
                 T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
                 TF::r2r_store(&regs[(size_t)tid * E], TF::slot_of(tid), gout, out_ns, valid, (T)prm.scale, prm.flip != 0);
             }
-        } else if (MODE == 1 || MODE == 3) {
+        } else if (MODE == 1 || MODE == 3 || MODE == 5) {
             // __syncthreads()
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 const C* v = &regs[(size_t)tid * E];
@@ -467,7 +490,11 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
             for (int tid = 0; tid < TF::THREADS; ++tid) {
                 long long o, i; bool valid;
                 coords(tid, o, i, valid);
-                if (MODE == 3) {
+                if (MODE == 5) {
+                    T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
+                    TF::r2r1_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), gout, out_ns, valid, (T)prm.scale,
+                                  prm.flip != 0);
+                } else if (MODE == 3) {
                     T* gout = reinterpret_cast<T*>(prm.out) + o * prm.out_ostride + i;
                     TF::r2r_post(TF::pencil_of(tid), TF::slot_of(tid), smem.data(), rtw.data(), qtw.data(), gout, out_ns, valid,
                                  (T)prm.scale, prm.flip != 0);
@@ -504,12 +531,16 @@ static int emu_real_one(const FftParams& prm_in, long long outer) {
     if (n == N) return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 1>(prm, outer) \
                      : mode == 3 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 3>(prm, outer) \
                      : mode == 4 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 4>(prm, outer) \
+                     : mode == 5 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 5>(prm, outer) \
+                     : mode == 6 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 6>(prm, outer) \
                                  : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P, false, PS, 2>(prm, outer);
 #define EMU_REAL_STRIDED(N, E, P, PS, MINB, ...)                                                         \
     if (n == N)                                                                                          \
         return mode == 1 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 1>(prm, outer) \
              : mode == 3 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 3>(prm, outer) \
              : mode == 4 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 4>(prm, outer) \
+             : mode == 5 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 5>(prm, outer) \
+             : mode == 6 ? emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 6>(prm, outer) \
                          : emu_real_one<T, N, E, Radices<__VA_ARGS__>, P * (int)(sizeof(double) / sizeof(T)), true, PS, 2>(prm, outer);
 
 template <class T>
@@ -917,14 +948,35 @@ extern "C" int emu_fft_trunc(int precision, int kind, int n, int keep, long long
 // kind = FFTW integer 5 (REDFT10), 4 (REDFT01), 9 (RODFT10), 8 (RODFT01).  Strides as capi.cu run_plan sets them.
 extern "C" int emu_fft_r2r(int precision, int kind, int n, long long outer, long long inner, const void* in, void* out,
                            double scale) {
-    if (n % 2 || (kind != 5 && kind != 4 && kind != 9 && kind != 8)) return -2;
+    if (kind == 3 || kind == 7) {
+        // kinds I: N = n - 1 (REDFT00) / n + 1 (RODFT00) complex points
+        FftParams prm;
+        std::memset(&prm, 0, sizeof(prm));
+        prm.in = in;
+        prm.out = out;
+        prm.scale = scale;
+        prm.flip = kind == 7;
+        const bool strided = inner > 1;
+        if (strided) {
+            prm.in_ostride = prm.out_ostride = (long long)n * inner;
+            prm.in_nstride = prm.out_nstride = inner;
+            prm.inner = inner;
+        } else {
+            prm.in_ostride = prm.out_ostride = n;
+            prm.npencils = outer;
+        }
+        const int nc = kind == 3 ? n - 1 : n + 1;
+        if (precision == 8) return emu_real_dispatch<double>(nc, 5, strided, prm, outer);
+        return emu_real_dispatch<float>(nc, 5, strided, prm, outer);
+    }
+    if (n % 2 || (kind != 5 && kind != 4 && kind != 9 && kind != 8 && kind != 6 && kind != 10)) return -2;
     FftParams prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.in = in;
     prm.out = out;
     prm.scale = scale;
-    prm.flip = (kind == 9 || kind == 8) ? 1 : 0;
-    const int mode = (kind == 5 || kind == 9) ? 3 : 4;
+    prm.flip = (kind == 9 || kind == 8 || kind == 10) ? 1 : 0;
+    const int mode = (kind == 6 || kind == 10) ? 6 : (kind == 5 || kind == 9) ? 3 : 4;
     const bool strided = inner > 1;
     if (strided) {
         prm.in_ostride = prm.out_ostride = (long long)n * inner;

@@ -423,10 +423,11 @@ def test_errors(B):
 
 @pytest.mark.parametrize('n', [4, 8, 64, 256, 1024, 4096, 96, 768, 160, 1280, 112, 896])
 @pytest.mark.parametrize('dt', ['d', 'f'])
-def test_stockham_r2r_kinds_2_and_3(B, n, dt):
-    """DCT / DST of kinds II and III (FFTW_REDFT10 / REDFT01 / RODFT10 / RODFT01,
-    /root/reference/mpi4py_fft/fftw/xfftn.py:14-36) of even length as Stockham real transforms
-    (Makhoul permutation + n/2-point complex schedule + quarter-wave twiddle) against scipy:
+def test_stockham_r2r_kinds_2_3_4(B, n, dt):
+    """DCT / DST of kinds II, III and IV (FFTW_REDFT10 / REDFT01 / REDFT11 and the RODFT ones,
+    /root/reference/mpi4py_fft/fftw/xfftn.py:14-36) of even length as Stockham transforms
+    (II / III: Makhoul permutation + n/2-point complex schedule + quarter-wave twiddle; IV: n/2-point
+    transform of pre-twiddled pairs) against scipy:
     contiguous and strided axes, ragged tiles, in place, inverse pairs, and the chirp-z kernels
     (r2r_engine=1) as a second witness on the same input"""
     from mpi4py_fft_b200 import _lib
@@ -436,7 +437,7 @@ def test_stockham_r2r_kinds_2_and_3(B, n, dt):
     for shape in shapes:
         axis = shape.index(n)
         x = rand(shape, dt, seed=n + axis)
-        for typ in (2, 3):
+        for typ in (2, 3, 4):
             for fam, planner, iplanner in (('dct', fftw.dctn, fftw.idctn), ('dst', fftw.dstn, fftw.idstn)):
                 A = fftw.aligned(shape, dtype=dt)
                 A[...] = x
@@ -460,3 +461,25 @@ def test_stockham_r2r_kinds_2_and_3(B, n, dt):
                         assert relerr(c(), y) < tol
                     finally:
                         _lib.set_option('r2r_engine', 0)
+
+
+@pytest.mark.parametrize('N', [4, 8, 64, 256, 1024, 96, 160, 112])
+@pytest.mark.parametrize('dt', ['d', 'f'])
+def test_stockham_r2r_kinds_1(B, N, dt):
+    """DCT-I of N + 1 points (the Chebyshev grids 2^k + 1) and DST-I of N - 1 points (FFTW_REDFT00 / RODFT00)
+    as the real transform of the even / odd extension of length 2N, read through an index map"""
+    fftw = B.fftw
+    tol = TOL[dt] * (10 if dt == 'f' else 1) * max(1.0, np.log2(N) / 4)
+    for fam, planner, iplanner, n in (('dct', fftw.dctn, fftw.idctn, N + 1), ('dst', fftw.dstn, fftw.idstn, N - 1)):
+        for shape in ((5, n), (3, n, 7), (n, 9)):
+            axis = shape.index(n)
+            x = rand(shape, dt, seed=n + axis)
+            A = fftw.aligned(shape, dtype=dt)
+            A[...] = x
+            p = planner(A, axes=(axis,), type=1)
+            assert 'stockham-r2r' in p.plan().describe(), (n, fam)
+            y = np.asarray(p()).copy()
+            ref = getattr(sfft, fam)(x.astype('d'), type=1, axis=axis)
+            assert relerr(y, ref) < tol, (fam, n, shape)
+            ip = iplanner(p.output_array, axes=(axis,), type=1, output_array=A)
+            assert relerr(ip(normalize=True), x.astype('d')) < tol, ('inverse', fam, n, shape)
