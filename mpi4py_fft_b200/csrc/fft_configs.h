@@ -173,7 +173,8 @@
 //           log2(first radix); 30 = none)
 //   MINB    min CTAs per SM  +  16 * OPT   (OPT bit 0: pass twiddles live in shared
 //           memory; bit 1: cp.async requests of the next tile are spread over the
-//           current tile's phases; bit 2: L2 prefetch of the tile after next) -- fft_tma.cuh
+//           current tile's phases; bit 2: L2 prefetch of the tile after next; bit 3 (cp.async table only): results leave through
+//           shared memory and TMA tensor stores) -- fft_tma.cuh
 #define B2F_TMA_TABLE_A(X) \
     X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8) \
     X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8) \
@@ -240,6 +241,7 @@
     X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32) \
     X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8) \
     X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32) \
+    X(1024, 7, 32, 8, 5, 1, 1, 145, 32, 32) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8) \
     X(2048, 1, 32, 4, 5, 1, 1, 17, 32, 8, 8) \
     X(2048, 2, 32, 4, 5, 1, 1, 1, 32, 8, 8) \

@@ -76,55 +76,7 @@ static B2F_HD void load_rows(typename TF::C* v, int p, int q, const typename TF:
     }
 }
 
-// Output staging of the TMA-store flavour (OPT bit 3): the last pass writes its
-// results into the (then idle) exchange buffer as dense rows [n][P] and the TMA
-// engine stores them (cp.async.bulk.tensor, boxes of P elements x <= 256 rows)
-// while the CTA already works on the next tile.  A buffer smaller than the tile
-// takes the rows in COUNT chunks of ROWS consecutive rows.
-template <class TF, class EX>
-struct OutChunks {
-    static constexpr int fit = (int)(EX::bytes / (sizeof(typename TF::C) * TF::PEN));
-    static constexpr int count = fit >= TF::LEN ? 1 : fit >= TF::LEN / 2 ? 2 : fit >= TF::LEN / 4 ? 4 : 8;
-    static constexpr int rows = TF::LEN / count;
-    static constexpr int box_rows = rows > 256 ? 256 : rows;
-    static_assert(TF::RADS::get(TF::NPASS - 1) % count == 0, "last radix must be a multiple of the chunk count");
-    static_assert(fit >= TF::LEN / 8, "exchange buffer too small to stage the output");
-};
-
-// results of the last pass that fall into chunk c -> staging rows (scaled, re/im swapped back)
-template <class TF, int COUNT>
-static B2F_HD void stage_out_rows(const typename TF::C* v, int p, int q, typename TF::C* xo, int c, bool swap,
-                                  typename TF::Real scale) {
-    using C = typename TF::C;
-    constexpr int R = TF::RADS::get(TF::NPASS - 1);
-    constexpr int NB = TF::EPT / R;
-    constexpr int ROWS = TF::LEN / COUNT;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if ((r * COUNT) / R == c) {
-                const int n = q + b * TF::TP + r * (TF::LEN / R);
-                C a = v[b * R + r];
-                a.x *= scale;
-                a.y *= scale;
-                if (swap) { auto t = a.x; a.x = a.y; a.y = t; }
-                xo[(n - c * ROWS) * TF::PEN + p] = a;
-            }
-        }
-    }
-}
-
 #if defined(__CUDACC__)
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// every committed bulk store has READ its shared-memory source (the buffer may be rewritten)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile(

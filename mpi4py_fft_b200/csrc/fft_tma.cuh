@@ -153,6 +153,58 @@ static B2F_HD void load_stage(typename TF::C* v, int p, int q, const typename TF
     }
 }
 
+// Output staging of the TMA-store flavour (OPT bit 3): the last pass writes its
+// results into the (then idle) exchange buffer as dense rows [n][P] and the TMA
+// engine stores them (cp.async.bulk.tensor, boxes of P elements x <= 256 rows)
+// while the CTA already works on the next tile.  A buffer smaller than the tile
+// takes the rows in COUNT chunks of ROWS consecutive rows.
+template <class TF, class EX>
+struct OutChunks {
+    static constexpr int fit = (int)(EX::bytes / (sizeof(typename TF::C) * TF::PEN));
+    static constexpr int count = fit >= TF::LEN ? 1 : fit >= TF::LEN / 2 ? 2 : fit >= TF::LEN / 4 ? 4 : 8;
+    static constexpr int rows = TF::LEN / count;
+    static constexpr int box_rows = rows > 256 ? 256 : rows;
+    static_assert(TF::RADS::get(TF::NPASS - 1) % count == 0, "last radix must be a multiple of the chunk count");
+    static_assert(fit >= TF::LEN / 8, "exchange buffer too small to stage the output");
+};
+
+// results of the last pass that fall into chunk c -> staging rows (scaled, re/im swapped back)
+template <class TF, int COUNT>
+static B2F_HD void stage_out_rows(const typename TF::C* v, int p, int q, typename TF::C* xo, int c, bool swap,
+                                  typename TF::Real scale) {
+    using C = typename TF::C;
+    constexpr int R = TF::RADS::get(TF::NPASS - 1);
+    constexpr int NB = TF::EPT / R;
+    constexpr int ROWS = TF::LEN / COUNT;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if ((r * COUNT) / R == c) {
+                const int n = q + b * TF::TP + r * (TF::LEN / R);
+                C a = v[b * R + r];
+                a.x *= scale;
+                a.y *= scale;
+                if (swap) { auto t = a.x; a.x = a.y; a.y = t; }
+                xo[(n - c * ROWS) * TF::PEN + p] = a;
+            }
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk store has READ its shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+#endif  // __CUDACC__
+
 #if defined(__CUDACC__)
 
 template <class TF, class EX, int S>
@@ -187,8 +239,13 @@ struct TmaMid {
 // beside a ~200 KiB carve-out does not keep them); bit 1: the cp.async loader
 // spreads the next tile's requests over the current tile's phases instead of
 // issuing them in one burst (LSU queue pressure)
+// bit 3: results leave through the exchange buffer and TMA tensor stores (UTMASTG) instead of per-thread
+// STG: the store burst of a tile no longer stalls every warp on the LSU queue, it drains while the next
+// tile is computed -- and goes through the TMA unit's address path while the loads use the LSU's
 template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int LOADER, bool SWAP, bool PEER, int OPT>
-__device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const TmaParams& prm) {
+__device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const TmaParams& prm,
+                                             const CUtensorMap* map_out = nullptr) {
+    constexpr bool TSTORE = (OPT & 8) != 0 && !PEER;
     using TF = TileFFT<T, N, E, RAD, P, true, PS>;
     using EX = Exchange<TF, SPLIT>;
     using C = cplx<T>;
@@ -297,6 +354,7 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
             __syncthreads();   // everybody's copies of this tile have landed
         }
         load_stage<TF>(v, p, q, stages + (size_t)s * N * P, SWAP);
+        if (TSTORE && tid == 0) bulk_wait_read();   // the previous tile's TMA stores have read the exchange buffer
         __syncthreads();   // every thread has read stage s (and finished with the exchange buffer of the previous tile)
         const long long tn = t + (long long)STAGES * step;
         if (LOADER == 0) {
@@ -316,6 +374,24 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
             long long part = 0, rest = 0;
             if (valid) prm.peer.locate(o, i, &part, &rest);
             TF::store_peer(v, q, prm.peer, part, rest, valid, SWAP, (T)prm.scale);
+        } else if constexpr (TSTORE) {
+            using OC = OutChunks<TF, EX>;
+            C* xo = reinterpret_cast<C*>(xbuf);
+            const int i0 = (int)((t - o * prm.tiles_per_outer) * P);
+#pragma unroll
+            for (int c = 0; c < OC::count; ++c) {
+                if (c > 0 && tid == 0) bulk_wait_read();
+                __syncthreads();   // exchange reads (c = 0) / the TMA reads of the previous chunk are done
+                stage_out_rows<TF, OC::count>(v, p, q, xo, c, SWAP, (T)prm.scale);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+#pragma unroll
+                    for (int k = 0; k < OC::rows; k += OC::box_rows)
+                        tma_store_4d(map_out, xo + (size_t)k * P, 2 * i0, c * OC::rows + k, (int)o, 0);
+                    bulk_commit();
+                }
+            }
         } else {
             TF::store_global(v, q, gout, prm.out_nstride, valid, SWAP, (T)prm.scale);
         }
@@ -324,6 +400,7 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
             parity ^= 1;
         }
     }
+    if (TSTORE && tid == 0) bulk_wait_all();   // shared memory stays alive until the last store has left
 }
 
 template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
@@ -337,6 +414,14 @@ __global__ void __launch_bounds__((N / E) * P, (MO & 15))
 fft_tma_peer_kernel(const __grid_constant__ CUtensorMap map_in, const TmaParams prm) {
     if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, true, true, (MO >> 4)>(&map_in, prm);
     else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 0, false, true, (MO >> 4)>(&map_in, prm);
+}
+
+// cp.async loader + TMA tensor stores (OPT bit 3 of MO): the descriptor describes the OUTPUT
+template <class T, int N, int E, class RAD, int P, int PS, int STAGES, bool SPLIT, int MO>
+__global__ void __launch_bounds__((N / E) * P, (MO & 15))
+fft_cpa_ts_kernel(const __grid_constant__ CUtensorMap map_out, const TmaParams prm) {
+    if (prm.swap) fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, true, false, (MO >> 4)>(nullptr, prm, &map_out);
+    else fft_tma_body<T, N, E, RAD, P, PS, STAGES, SPLIT, 1, false, false, (MO >> 4)>(nullptr, prm, &map_out);
 }
 
 // the same pipeline with the cp.async loader (no descriptor)

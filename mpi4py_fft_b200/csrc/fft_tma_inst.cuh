@@ -76,6 +76,35 @@ static cudaError_t launch_cpa_one(const TmaStep& st, cudaStream_t stream) {
     long long grid = (long long)sm_count() * ctas_per_sm;
     if (st.grid_cap > 0 && grid > (long long)st.grid_cap * ctas_per_sm) grid = (long long)st.grid_cap * ctas_per_sm;
     if (grid > prm.ntiles) grid = prm.ntiles;
+    if constexpr (((MINB >> 4) & 8) != 0) {
+        // TMA-store flavour: whole-block launches without a fused peer store only
+        if (peer || st.pitch || st.ostride) return cudaErrorInvalidValue;
+        using OC = OutChunks<TF, EX>;
+        auto kts = fft_cpa_ts_kernel<T, N, E, RAD, P, PS, STAGES, SPLIT, MINB>;
+        static bool ts_attr = false;
+        if (!ts_attr) {
+            cudaError_t e = cudaFuncSetAttribute(kts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            ts_attr = true;
+        }
+        TensorMapEncodeFn enc = tensor_map_encoder();
+        if (!enc) return cudaErrorNotSupported;
+        const size_t esz = sizeof(cplx<T>);
+        if (((uintptr_t)st.out & 15) || (st.inner * esz) % 16 || 2 * st.inner >= (1LL << 32)) return cudaErrorInvalidValue;
+        CUtensorMap map;
+        const cuuint64_t dims[4] = {(cuuint64_t)(2 * st.inner), (cuuint64_t)N, (cuuint64_t)st.outer, 1};
+        const cuuint64_t strides[3] = {(cuuint64_t)(st.inner * esz), (cuuint64_t)(st.inner * esz) * N,
+                                       (cuuint64_t)(st.inner * esz) * N * (cuuint64_t)st.outer};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * P), (cuuint32_t)OC::box_rows, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         st.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+        kts<<<(unsigned)grid, TF::THREADS, smem, stream>>>(map, prm);
+        count_launch();
+        return cudaGetLastError();
+    }
     kern<<<(unsigned)grid, TF::THREADS, smem, stream>>>(prm);
     count_launch();
     return cudaGetLastError();
