@@ -26,6 +26,7 @@
 #include "fft_configs.h"
 #include "chirpz_host.h"
 #include "rot_plan.h"
+#include "lengths.h"
 
 #define B2F_GENERIC_MAX_N 4096
 
@@ -170,7 +171,7 @@ static const ChirpEntry* chirp_tables(int kind, long long n, int precision) {
 }
 
 // ---- plan ------------------------------------------------------------------
-enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1, STEP_REAL = 2, STEP_CHIRP = 3 };
+enum StepType { STEP_POW2 = 0, STEP_GENERIC = 1, STEP_REAL = 2, STEP_CHIRP = 3, STEP_FOURSTEP = 4 };
 enum Buf { BUF_IN = 0, BUF_OUT = 1 };
 
 struct Step {
@@ -188,6 +189,9 @@ struct Step {
     int rows, cols;
     // chirp-z
     const void* chirp;
+    // four-step split (lengths.h): n = n1 * n2, `sub` = the plan of the n2-point transforms along j2
+    long long n1, n2;
+    ::b2f_plan_s* sub;
 };
 
 // Default variant of the staged strided kernels (fft_configs.h B2F_TMA_TABLE /
@@ -224,17 +228,6 @@ static int staged_fallback(int n, int precision) {
         default: return -1;
     }
 }
-
-static bool is_pow2(long long n) { return n >= 2 && (n & (n - 1)) == 0; }
-// 3 * 2^k, 3 <= n <= 6144: served by the radix-3/6/12/24 schedules
-static bool is_mixed(long long n) { return n >= 3 && n <= B2F_MIXED_MAX_N && n % 3 == 0 && (n == 3 || is_pow2(n / 3)); }
-// 5 * 2^k <= 1280 and 7 * 2^k <= 1792: the radix-5/10/20 and radix-7/14/28 schedules
-static bool is_mixed57(long long n) {
-    if (n >= 5 && n <= B2F_MIXED5_MAX_N && n % 5 == 0 && (n == 5 || is_pow2(n / 5))) return true;
-    return n >= 7 && n <= B2F_MIXED7_MAX_N && n % 7 == 0 && (n == 7 || is_pow2(n / 7));
-}
-// lengths with a Stockham kernel instance
-static bool is_stockham(long long n) { return (is_pow2(n) && n <= B2F_POW2_MAX_N) || is_mixed(n) || is_mixed57(n); }
 
 // does the chirp-z convolution of this transform fit the largest tile (M <= 8192)?
 static bool chirp_fits(int kind, long long n) {
@@ -279,9 +272,24 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     s.dst = dst;
     // logical transform length: the real side for r2c / c2r
     const long long n = (kind == B2F_C2R) ? s.n_out : s.n_in;
+    FourStep fs;
     if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && is_stockham(n) && option("stockham", 1)) {
         s.type = STEP_POW2;
         s.swap = (kind == B2F_BACKWARD);
+    } else if ((kind == B2F_FORWARD || kind == B2F_BACKWARD) && !is_stockham(n) && !chirp_fits(kind, n) &&
+               option("stockham", 1) && fourstep_split(n, &fs)) {
+        // beyond one tile (2^k > 8192, other lengths > 4096): two transforms of lengths that have kernels
+        s.type = STEP_FOURSTEP;
+        s.swap = (kind == B2F_BACKWARD);
+        s.n1 = fs.n1;
+        s.n2 = fs.n2;
+        // step 1 as a plan of its own: the block viewed (outer, n2, n1 * inner), transform along the middle axis
+        const int64_t v[3] = {(int64_t)s.outer, (int64_t)fs.n2, (int64_t)(fs.n1 * s.inner)};
+        const int ax = 1;
+        b2f_plan sub = nullptr;
+        const int rc = b2f_planxfftn(&sub, 3, v, v, 1, &ax, &kind, pl->precision, 0);
+        if (rc) return rc;
+        s.sub = sub;
     } else if ((kind == B2F_R2C || kind == B2F_C2R) && n >= 4 && n % 2 == 0 && is_stockham(n / 2) &&
                option("real_engine", 0) != 1 && option("stockham", 1)) {
         // even-length real transform = n/2-point complex Stockham + split/merge pass
@@ -331,8 +339,8 @@ static int add_step(b2f_plan_s* pl, int kind, int axis, const std::vector<long l
     } else {
         if (n > B2F_GENERIC_MAX_N) {
             set_error("transform length " + std::to_string(n) + " of kind " + std::to_string(kind) +
-                      " is not supported by this build (c2c: 2^k <= 8192 and 3*2^k <= 6144; r2c/c2r: twice those; "
-                      "any other length / kind up to 4096)");
+                      " is not supported by this build (c2c: every length with a Stockham kernel, products n1 * n2 of a 2^k "
+                      "in 64..2048 and such a length, any other length up to 4096; r2c/c2r: twice a Stockham length or <= 4096)");
             return B2F_EUNSUPPORTED;
         }
         s.type = STEP_GENERIC;
@@ -444,8 +452,18 @@ int b2f_planxfftn(b2f_plan* plan, int ndims, const int64_t* sizes_in, const int6
                           i == naxes - 1 ? BUF_IN : BUF_OUT, BUF_OUT);
         }
     }
+    if (rc == B2F_OK)
+        for (const Step& st : pl->steps)
+            if (st.type == STEP_FOURSTEP) {
+                long long elems = 1;
+                for (int i = 0; i < ndims; ++i) elems *= sizes_in[i];
+                const size_t need = (size_t)elems * 2 * precision;
+                if (need > pl->scratch_bytes) pl->scratch_bytes = need;
+            }
     if (rc != B2F_OK) {
         if (rc == B2F_EINVAL && g_err.empty()) set_error("b2f_planxfftn: sizes_in/sizes_out/kind are inconsistent");
+        for (Step& st : pl->steps)
+            if (st.sub) b2f_destroy_plan(st.sub);
         delete pl;
         return rc;
     }
@@ -719,6 +737,56 @@ int run_plan(b2f_plan pl, const void* d_in, void* d_out, double scale, cudaStrea
                 e = launch(var);
                 if (e == cudaErrorInvalidValue && var != 0 && !strict) e = launch(0);   // variant not built for this n
             }
+        } else if (s.type == STEP_FOURSTEP) {
+            if (peer || (chunk && chunk->mode != 0)) {
+                set_error("a four-step stage can neither scatter nor run in pieces");
+                return B2F_EUNSUPPORTED;
+            }
+            if (!pl->scratch) {
+                cudaError_t ce = cudaMalloc(&pl->scratch, pl->scratch_bytes);
+                if (ce != cudaSuccess) {
+                    pl->scratch = nullptr;
+                    return cuda_fail(ce, "cudaMalloc(four-step scratch)");
+                }
+            }
+            const long long n1 = s.n1, n2 = s.n2, nn = s.n_in;
+            const size_t esz = 2 * (size_t)pl->precision;
+            // 1: n2-point transforms along j2 (stride n1 * inner): src -> scratch
+            int rc = run_plan(s.sub, src, pl->scratch, 1.0, st, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            // 2: twiddle W_n^(j1 k2)
+            e = launch_fourstep_twiddle(pl->precision, pl->scratch, s.outer, n2, n1, s.inner, s.swap ? 1 : 0, st);
+            if (e != cudaSuccess) return cuda_fail(e, "four-step twiddle kernel");
+            // 3: n1-point transforms along j1 for every k2, stored k1-major: X[n2 k1 + k2]
+            if (s.inner == 1) {
+                // rows of n1 contiguous points in, transposed out: the rotating kernel with I = n2, O = 1
+                RotStep rs{pl->scratch, dst, s.outer, n2, 1, n1, n1, nn, nn, n2, nn, sc, s.swap ? 1 : 0, 0};
+                e = launch_rot(pl->precision, (int)n1, rot_default((int)n1), rs, st);
+            } else {
+                FftParams prm;
+                memset(&prm, 0, sizeof(prm));
+                prm.scale = sc;
+                prm.swap = s.swap ? 1 : 0;
+                prm.in_ostride = n1 * s.inner;     // k2 -> k2 + 1 in the scratch
+                prm.in_nstride = s.inner;          // j1 -> j1 + 1
+                prm.out_ostride = s.inner;         // k2 -> k2 + 1 in the result
+                prm.out_nstride = n2 * s.inner;    // k1 -> k1 + 1
+                prm.inner = s.inner;
+                e = cudaSuccess;
+                for (long long o = 0; o < s.outer && e == cudaSuccess; ++o) {
+                    prm.in = (const char*)pl->scratch + (size_t)o * nn * s.inner * esz;
+                    prm.out = (char*)dst + (size_t)o * nn * s.inner * esz;
+                    const int n1i = (int)n1;
+                    if (pl->precision == 8)
+                        e = n1i <= 256 ? launch_pow2_small_f64(n1i, 0, true, prm, n2, st)
+                          : n1i <= 1024 ? launch_pow2_mid_f64(n1i, 0, true, prm, n2, st)
+                                        : launch_pow2_large_f64(n1i, 0, true, prm, n2, st);
+                    else
+                        e = n1i <= 256 ? launch_pow2_small_f32(n1i, 0, true, prm, n2, st)
+                          : n1i <= 1024 ? launch_pow2_mid_f32(n1i, 0, true, prm, n2, st)
+                                        : launch_pow2_large_f32(n1i, 0, true, prm, n2, st);
+                }
+            }
         } else if (s.type == STEP_REAL) {
             if (peer) {
                 set_error("fused redistribution needs a power-of-two c2c Stockham step last");
@@ -820,6 +888,9 @@ extern "C" {
 
 int b2f_destroy_plan(b2f_plan pl) {
     if (pl && pl->scratch) cudaFree(pl->scratch);
+    if (pl)
+        for (Step& st : pl->steps)
+            if (st.sub) b2f_destroy_plan(st.sub);
     delete pl;   // tables are cached library-wide
     return B2F_OK;
 }
@@ -830,7 +901,8 @@ int b2f_plan_describe(b2f_plan pl, char* buf, size_t buflen) {
     for (const Step& st : pl->steps) {
         char line[256];
         snprintf(line, sizeof(line), "%s kind=%d axis=%d n_in=%lld n_out=%lld outer=%lld inner=%lld %s->%s\n",
-                 st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig")
+                 st.type == STEP_FOURSTEP ? "stockham-fourstep"
+                 : st.type == STEP_POW2 ? (st.inner > 1 ? "stockham-strided" : "stockham-contig")
                  : st.type == STEP_REAL ? (st.kind >= B2F_REDFT00 ? (st.inner > 1 ? "stockham-r2r-strided" : "stockham-r2r-contig")
                                                                    : (st.inner > 1 ? "stockham-real-strided" : "stockham-real-contig"))
                  : st.type == STEP_CHIRP ? (st.inner > 1 ? "chirpz-strided" : "chirpz-contig") : "dense-matrix",

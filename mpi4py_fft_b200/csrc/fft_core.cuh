@@ -66,6 +66,21 @@ B2F_HD cplx<T> mul_w32(cplx<T> a, int s) {
     return {a.x * c + a.y * sn, a.y * c - a.x * sn};
 }
 
+// four-step twiddle W_n^m (m already reduced modulo n), forward sign -1 / backward +1; the angle is
+// formed in double for both precisions
+template <class T>
+B2F_HD cplx<T> fourstep_twiddle(long long m, long long n, bool backward) {
+    const double a = 2.0 * (double)m / (double)n;   // in units of pi
+    double sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincospi(a, &sn, &cs);
+#else
+    sn = sin(3.14159265358979323846 * a);
+    cs = cos(3.14159265358979323846 * a);
+#endif
+    return {(T)cs, (T)(backward ? sn : -sn)};
+}
+
 // ---------------------------------------------------------------------------
 // R-point forward DFT on registers, natural order in and out (R = 2..32).
 // Decimation in time by two; all indices are compile-time constants after

@@ -53,6 +53,9 @@ struct TmaStep {
 cudaError_t launch_tma_f64(int n, int var, const TmaStep& st, cudaStream_t stream);
 cudaError_t launch_tma_f32(int n, int var, const TmaStep& st, cudaStream_t stream);
 int sm_count();   // SMs of the current device (cached)
+// twiddle pass of a four-step split (fourstep.cu): data viewed (outer, n2, n1, inner), times W_(n1 n2)^(j1 k2)
+cudaError_t launch_fourstep_twiddle(int precision, void* data, long long outer, long long n2, long long n1, long long inner,
+                                    int backward, cudaStream_t st);
 
 // rotating c2c kernels (fft_rot_*.cu): transform the contiguous axis of in[b][i][o][n]
 // (pencil (i, o) of batch b starts at b*in_bstride + i*in_istride + o*in_ostride) and

@@ -989,3 +989,66 @@ extern "C" int emu_fft_r2r(int precision, int kind, int n, long long outer, long
     if (precision == 8) return emu_real_dispatch<double>(n / 2, mode, strided, prm, outer);
     return emu_real_dispatch<float>(n / 2, mode, strided, prm, outer);
 }
+
+// ---- four-step split of a c2c length beyond one tile (csrc/lengths.h fourstep_split, capi.cu STEP_FOURSTEP):
+// (outer, n, inner) block, n = n1 * n2.  Step 1: n2-point transforms along j2 of the (outer, n2, n1 * inner) view,
+// in -> scratch; step 2: twiddle; step 3: n1-point transforms stored k1-major -- the rotating kernel when the axis
+// is contiguous, the strided kernel with transposed output strides otherwise.  Same parameters as capi.cu.
+#include "../../mpi4py_fft_b200/csrc/lengths.h"
+template <class T>
+static int emu_fourstep_t(int precision, long long n, long long outer, long long inner, const void* in, void* out,
+                          void* scratch, double scale, int swap, long long* n1_out, long long* n2_out) {
+    FourStep fs;
+    if (is_stockham(n) || !fourstep_split(n, &fs)) return -1;
+    *n1_out = fs.n1;
+    *n2_out = fs.n2;
+    const long long n1 = fs.n1, n2 = fs.n2;
+    // 1
+    FftParams p1;
+    std::memset(&p1, 0, sizeof(p1));
+    p1.in = in;
+    p1.out = scratch;
+    p1.scale = 1.0;
+    p1.swap = swap;
+    p1.in_ostride = p1.out_ostride = n2 * n1 * inner;
+    p1.in_nstride = p1.out_nstride = n1 * inner;
+    p1.inner = n1 * inner;
+    int rc = emu_dispatch<T>((int)n2, 0, true, p1, outer);
+    if (rc) return rc;
+    // 2
+    cplx<T>* sc = reinterpret_cast<cplx<T>*>(scratch);
+    const long long total = outer * n2 * n1 * inner;
+    for (long long idx = 0; idx < total; ++idx) {
+        long long t = idx / inner;
+        const long long j1 = t % n1;
+        t /= n1;
+        const long long k2 = t % n2;
+        sc[idx] = cmul(sc[idx], fourstep_twiddle<T>((j1 * k2) % n, n, swap != 0));
+    }
+    // 3
+    if (inner == 1) {
+        EmuRotStep st{scratch, out, outer, n2, 1, n1, n1, n, n, n2, n, scale, swap};
+        return emu_rot_dispatch<T>((int)n1, rot_default((int)n1), st);
+    }
+    FftParams p3;
+    std::memset(&p3, 0, sizeof(p3));
+    p3.scale = scale;
+    p3.swap = swap;
+    p3.in_ostride = n1 * inner;
+    p3.in_nstride = inner;
+    p3.out_ostride = inner;
+    p3.out_nstride = n2 * inner;
+    p3.inner = inner;
+    for (long long o = 0; o < outer; ++o) {
+        p3.in = (const char*)scratch + (size_t)o * n * inner * 2 * precision;
+        p3.out = (char*)out + (size_t)o * n * inner * 2 * precision;
+        rc = emu_dispatch<T>((int)n1, 0, true, p3, n2);
+        if (rc) return rc;
+    }
+    return 0;
+}
+extern "C" int emu_fourstep(int precision, long long n, long long outer, long long inner, const void* in, void* out,
+                            void* scratch, double scale, int swap, long long* n1_out, long long* n2_out) {
+    if (precision == 8) return emu_fourstep_t<double>(precision, n, outer, inner, in, out, scratch, scale, swap, n1_out, n2_out);
+    return emu_fourstep_t<float>(precision, n, outer, inner, in, out, scratch, scale, swap, n1_out, n2_out);
+}

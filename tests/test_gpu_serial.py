@@ -483,3 +483,39 @@ def test_stockham_r2r_kinds_1(B, N, dt):
             assert relerr(y, ref) < tol, (fam, n, shape)
             ip = iplanner(p.output_array, axes=(axis,), type=1, output_array=A)
             assert relerr(ip(normalize=True), x.astype('d')) < tol, ('inverse', fam, n, shape)
+
+
+@pytest.mark.parametrize('n', [16384, 32768, 65536, 12288, 10240, 7168, 1048576])
+@pytest.mark.parametrize('dt', ['D', 'F'])
+def test_fourstep_lengths_beyond_one_tile(B, n, dt):
+    """c2c lengths without a single-tile kernel (2^k > 8192, other lengths > 4096): the four-step split
+    n = n1 * n2 (csrc/lengths.h) -- strided n2-point transforms, twiddle, n1-point transforms stored
+    transposed (the rotating kernel on the contiguous axis) -- against numpy; FFTW plans any N
+    (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:49-56)"""
+    tol = TOL[dt.lower()] * 4
+    shapes = [(2, n), (n, 3), (2, n, 2)] if n <= 65536 else [(1, n)]
+    for shape in shapes:
+        axis = shape.index(n)
+        x = rand(shape, dt, seed=axis)
+        U = B.fftw.aligned(shape, dtype=dt)
+        U[...] = x
+        fwd = B.fftw.fftn(U, axes=(axis,))
+        assert 'stockham-fourstep' in fwd.plan().describe()
+        y = np.asarray(fwd(normalize=True)).copy()
+        ref = np.fft.fft(x.astype('D'), axis=axis) / n
+        assert relerr(y, ref) < tol, ('fwd', n, dt, shape)
+        assert np.array_equal(np.asarray(U), x)
+        bck = B.fftw.ifftn(fwd.output_array, axes=(axis,), output_array=U)
+        assert relerr(bck(), x.astype('D')) < tol, ('bwd', n, dt, shape)
+        V = B.fftw.aligned(shape, dtype=dt)
+        V[...] = x
+        B.fftw.fftn(V, axes=(axis,), output_array=V)()
+        assert relerr(V, ref * n) < tol, ('in place', n, dt, shape)
+    if n == 16384:
+        # inside a multi-axis stage
+        shape = (n, 64)
+        x = rand(shape, dt, seed=9)
+        U = B.fftw.aligned(shape, dtype=dt)
+        U[...] = x
+        y = B.fftw.fftn(U, axes=(0, 1))()
+        assert relerr(y, np.fft.fftn(x.astype('D'))) < tol
