@@ -125,9 +125,9 @@ B2F_API int b2f_pad_truncate(int mode, int half_spectrum, int precision,
  * (Nyquist rule included), the backward kernel's first pass reads them and takes zeros for the
  * rest, so the padded spectrum never exists in memory and the extra pass of b2f_pad_truncate
  * goes.  sizes_in / sizes_out given at plan time stay the padded ones.  Returns
- * B2F_EUNSUPPORTED when the plan's kernel family has no such flavour (c2c: lengths 3 * 2^k, the
- * sizes a 3/2-rule solver pads to; r2c / c2r: every Stockham length); the caller then runs
- * b2f_execute + b2f_pad_truncate.  n_keep = 0 switches it off.
+ * B2F_EUNSUPPORTED when the plan's kernel family has no such flavour (every single-tile Stockham
+ * r2c / c2r length and the 2^k and 3 * 2^k c2c lengths -- what a 3/2-rule or factor-2 padded solver
+ * transforms -- have one; 5 * 2^k / 7 * 2^k c2c, chirp-z, dense and four-step stages do not); the caller then runs b2f_execute + b2f_pad_truncate.  n_keep = 0 switches it off.
  * Replaces libfft.py:263-311 + 408-422 (truncate / pad, then scale) inside the FFT launch.
  */
 B2F_API int b2f_plan_set_truncation(b2f_plan plan, int64_t n_keep);

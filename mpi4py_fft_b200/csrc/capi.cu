@@ -488,10 +488,11 @@ int b2f_plan_set_truncation(b2f_plan pl, int64_t n_keep) {
         set_error("b2f_plan_set_truncation: kept modes must be in [1, padded modes]");
         return B2F_EINVAL;
     }
-    const bool ok = (s.type == STEP_POW2 && is_mixed(n)) || (s.type == STEP_REAL && s.kind < B2F_REDFT00);
+    // the 5 * 2^k / 7 * 2^k c2c kernels are built without the dealiasing flavour (build time)
+    const bool ok = (s.type == STEP_POW2 && !is_mixed57(n)) || (s.type == STEP_REAL && s.kind < B2F_REDFT00);
     if (!ok) {
-        set_error("this stage's kernel family has no dealiasing flavour (c2c: lengths 3 * 2^k; r2c / c2r: every "
-                  "Stockham length); use b2f_pad_truncate");
+        set_error("this stage's kernel family has no dealiasing flavour (only single-tile Stockham c2c / r2c / c2r "
+                  "stages have one); use b2f_pad_truncate");
         return B2F_EUNSUPPORTED;
     }
     pl->trunc_keep = n_keep;

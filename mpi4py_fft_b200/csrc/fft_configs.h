@@ -20,63 +20,37 @@
 #pragma once
 
 #define B2F_CONTIG_SMALL(X)               \
-    X(2, 0, 2, 128, 30, 1, 2)             \
-    X(4, 0, 4, 128, 30, 1, 4)             \
-    X(8, 0, 8, 64, 30, 1, 8)              \
-    X(16, 0, 16, 32, 30, 1, 16)           \
-    X(32, 0, 8, 32, 3, 1, 8, 4)           \
-    X(64, 0, 8, 16, 3, 1, 8, 8)           \
-    X(128, 0, 16, 16, 4, 1, 16, 8)        \
-    X(256, 0, 16, 8, 4, 1, 16, 16)        \
-    X(256, 1, 16, 4, 4, 1, 16, 16)        \
-    X(256, 2, 16, 2, 4, 1, 16, 16)
+    X(2, 0, 2, 128, 30, 1, 2) \
+    X(4, 0, 4, 128, 30, 1, 4) \
+    X(8, 0, 8, 64, 30, 1, 8) \
+    X(16, 0, 16, 32, 30, 1, 16) \
+    X(32, 0, 8, 32, 3, 1, 8, 4) \
+    X(64, 0, 8, 16, 3, 1, 8, 8) \
+    X(128, 0, 16, 16, 4, 1, 16, 8) \
+    X(256, 0, 16, 8, 4, 1, 16, 16)
 
 #define B2F_STRIDED_SMALL(X)              \
-    X(2, 0, 2, 128, 30, 1, 2)             \
-    X(4, 0, 4, 128, 30, 1, 4)             \
-    X(8, 0, 8, 64, 30, 1, 8)              \
-    X(16, 0, 16, 32, 30, 1, 16)           \
-    X(32, 0, 8, 32, 30, 1, 8, 4)          \
-    X(64, 0, 8, 16, 30, 1, 8, 8)          \
-    X(128, 0, 16, 16, 30, 1, 16, 8)       \
-    X(256, 0, 16, 8, 30, 1, 16, 16)       \
-    X(256, 1, 16, 16, 30, 1, 16, 16)      \
-    X(256, 2, 16, 32, 30, 1, 16, 16)
+    X(2, 0, 2, 128, 30, 1, 2) \
+    X(4, 0, 4, 128, 30, 1, 4) \
+    X(8, 0, 8, 64, 30, 1, 8) \
+    X(16, 0, 16, 32, 30, 1, 16) \
+    X(32, 0, 8, 32, 30, 1, 8, 4) \
+    X(64, 0, 8, 16, 30, 1, 8, 8) \
+    X(128, 0, 16, 16, 30, 1, 16, 8) \
+    X(256, 0, 16, 8, 30, 1, 16, 16) \
+    X(256, 1, 16, 16, 30, 1, 16, 16)
 
 #define B2F_CONTIG_MID(X)                 \
-    X(512, 0, 16, 4, 3, 1, 8, 8, 8)       \
-    X(512, 1, 8, 4, 3, 2, 8, 8, 8)        \
-    X(512, 2, 8, 2, 3, 4, 8, 8, 8)        \
-    X(512, 3, 8, 1, 3, 8, 8, 8, 8)        \
-    X(512, 4, 16, 2, 3, 1, 8, 8, 8)       \
-    X(512, 5, 16, 8, 3, 1, 8, 8, 8)       \
-    X(512, 6, 32, 8, 5, 1, 32, 16)        \
-    X(512, 7, 32, 4, 5, 1, 32, 16)        \
-    X(1024, 0, 16, 1, 4, 1, 16, 8, 8)     \
-    X(1024, 1, 16, 2, 4, 1, 16, 8, 8)     \
-    X(1024, 2, 16, 4, 4, 2, 16, 8, 8)     \
-    X(1024, 3, 32, 4, 5, 1, 32, 32)       \
-    X(1024, 4, 32, 2, 5, 1, 32, 32)       \
-    X(1024, 5, 32, 1, 5, 1, 32, 32)       \
-    X(1024, 6, 16, 8, 4, 1, 16, 8, 8)     \
-    X(1024, 7, 16, 4, 3, 2, 8, 8, 16)
+    X(512, 0, 16, 4, 3, 1, 8, 8, 8) \
+    X(512, 6, 32, 8, 5, 1, 32, 16) \
+    X(1024, 0, 16, 1, 4, 1, 16, 8, 8) \
+    X(1024, 3, 32, 4, 5, 1, 32, 32)
 
 #define B2F_STRIDED_MID(X)                \
-    X(512, 0, 16, 8, 30, 1, 8, 8, 8)      \
-    X(512, 1, 8, 4, 3, 2, 8, 8, 8)        \
-    X(512, 2, 8, 8, 30, 1, 8, 8, 8)       \
-    X(512, 3, 16, 16, 30, 1, 8, 8, 8)     \
-    X(512, 4, 16, 4, 3, 1, 8, 8, 8)       \
-    X(512, 5, 32, 8, 30, 1, 32, 16)       \
-    X(512, 6, 32, 16, 30, 1, 32, 16)      \
-    X(1024, 0, 16, 8, 30, 1, 16, 8, 8)    \
-    X(1024, 1, 16, 4, 4, 2, 16, 8, 8)     \
-    X(1024, 2, 32, 8, 30, 1, 32, 32)      \
-    X(1024, 3, 32, 4, 5, 1, 32, 32)       \
-    X(1024, 4, 16, 4, 4, 1, 16, 8, 8)     \
-    X(1024, 5, 16, 2, 4, 4, 16, 8, 8)     \
-    X(1024, 6, 16, 4, 4, 3, 16, 8, 8)     \
-    X(1024, 7, 16, 1, 4, 8, 16, 8, 8)
+    X(512, 0, 16, 8, 30, 1, 8, 8, 8) \
+    X(512, 3, 16, 16, 30, 1, 8, 8, 8) \
+    X(1024, 0, 16, 8, 30, 1, 16, 8, 8) \
+    X(1024, 1, 16, 4, 4, 2, 16, 8, 8)
 
 #define B2F_CONTIG_LARGE(X)               \
     X(2048, 0, 16, 2, 4, 1, 16, 16, 8)    \
@@ -177,35 +151,16 @@
 //           shared memory and TMA tensor stores) -- fft_tma.cuh
 #define B2F_TMA_TABLE_A(X) \
     X(64, 0, 8, 16, 30, 2, 0, 1, 8, 8) \
-    X(64, 1, 8, 16, 30, 2, 0, 17, 8, 8) \
     X(128, 0, 16, 16, 30, 2, 0, 1, 16, 8) \
     X(128, 1, 16, 8, 30, 2, 0, 1, 16, 8) \
-    X(128, 2, 16, 16, 30, 2, 0, 17, 16, 8) \
-    X(128, 3, 16, 8, 30, 2, 0, 17, 16, 8) \
-    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16) \
-    X(256, 1, 16, 16, 30, 2, 0, 1, 16, 16) \
-    X(256, 2, 16, 8, 30, 2, 0, 17, 16, 16) \
-    X(256, 3, 16, 16, 30, 2, 0, 17, 16, 16)
+    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16)
 
 #define B2F_TMA_TABLE_B(X) \
     X(512, 0, 16, 8, 3, 1, 1, 2, 8, 8, 8) \
-    X(512, 1, 32, 8, 5, 1, 1, 1, 32, 16) \
-    X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8) \
-    X(512, 3, 16, 4, 3, 2, 0, 1, 8, 8, 8) \
-    X(512, 4, 8, 8, 3, 1, 1, 1, 8, 8, 8) \
-    X(512, 5, 32, 8, 30, 2, 0, 1, 32, 16) \
-    X(512, 6, 32, 16, 5, 1, 1, 1, 32, 16) \
-    X(512, 7, 16, 16, 3, 1, 1, 1, 8, 8, 8) \
-    X(512, 8, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
-    X(512, 9, 32, 16, 5, 1, 1, 17, 32, 16)
+    X(512, 2, 16, 8, 30, 2, 0, 1, 8, 8, 8)
 
 #define B2F_TMA_TABLE_C(X) \
     X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32) \
-    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8) \
-    X(1024, 2, 16, 4, 4, 1, 1, 2, 16, 8, 8) \
-    X(1024, 3, 32, 4, 5, 1, 1, 1, 32, 32) \
-    X(1024, 4, 16, 4, 4, 2, 0, 1, 16, 8, 8) \
-    X(1024, 5, 32, 4, 5, 2, 0, 1, 32, 32) \
     X(1024, 6, 32, 8, 5, 1, 1, 17, 32, 32) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
@@ -213,39 +168,22 @@
 
 // the same pipeline filled by cp.async instead of TMA (variant_tma = 100 + VAR)
 #define B2F_CPA_TABLE_A(X) \
-    X(256, 0, 16, 8, 30, 2, 0, 1, 16, 16) \
-    X(256, 1, 16, 8, 30, 2, 0, 17, 16, 16) \
     X(256, 2, 16, 16, 30, 2, 0, 17, 16, 16) \
     X(256, 3, 16, 16, 30, 2, 0, 81, 16, 16) \
     X(192, 0, 24, 16, 30, 2, 0, 17, 24, 8) \
-    X(384, 0, 24, 8, 30, 2, 0, 17, 6, 8, 8) \
     X(384, 1, 24, 16, 30, 1, 0, 17, 6, 8, 8)
 
 #define B2F_CPA_TABLE_B(X) \
     X(512, 0, 16, 8, 30, 2, 0, 1, 8, 8, 8) \
-    X(512, 1, 32, 16, 5, 1, 1, 1, 32, 16) \
-    X(512, 2, 16, 16, 3, 1, 1, 1, 8, 8, 8) \
-    X(512, 3, 32, 16, 5, 1, 1, 49, 32, 16) \
-    X(512, 4, 16, 8, 30, 2, 0, 49, 8, 8, 8) \
     X(512, 5, 32, 16, 5, 1, 1, 17, 32, 16) \
-    X(512, 6, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
-    X(768, 0, 24, 8, 30, 1, 0, 17, 12, 8, 8) \
-    X(768, 1, 24, 8, 3, 1, 1, 17, 12, 8, 8) \
-    X(512, 7, 32, 16, 5, 1, 1, 81, 32, 16)
+    X(768, 0, 24, 8, 30, 1, 0, 17, 12, 8, 8)
 
 #define B2F_CPA_TABLE_C(X) \
     X(1024, 0, 32, 8, 5, 1, 1, 1, 32, 32) \
-    X(1024, 1, 16, 8, 4, 1, 1, 1, 16, 8, 8) \
     X(1024, 2, 32, 8, 5, 1, 1, 17, 32, 32) \
-    X(1024, 3, 32, 8, 5, 1, 1, 33, 32, 32) \
-    X(1024, 4, 32, 8, 5, 1, 1, 49, 32, 32) \
-    X(1024, 5, 16, 8, 4, 1, 1, 49, 16, 8, 8) \
-    X(1024, 6, 32, 8, 5, 1, 1, 81, 32, 32) \
     X(1024, 7, 32, 8, 5, 1, 1, 145, 32, 32) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8) \
-    X(2048, 1, 32, 4, 5, 1, 1, 17, 32, 8, 8) \
-    X(2048, 2, 32, 4, 5, 1, 1, 1, 32, 8, 8) \
-    X(2048, 3, 16, 2, 4, 1, 1, 17, 16, 16, 8)
+    X(2048, 2, 32, 4, 5, 1, 1, 1, 32, 8, 8)
 
 #define B2F_CPA_TABLE(X) B2F_CPA_TABLE_A(X) B2F_CPA_TABLE_B(X) B2F_CPA_TABLE_C(X)
 
@@ -259,26 +197,14 @@
 #define B2F_ROT_TABLE_A(X) \
     X(64, 0, 8, 16, 30, 2, 0, 20, 8, 8) \
     X(128, 0, 16, 16, 30, 2, 0, 18, 16, 8) \
-    X(128, 1, 16, 8, 30, 2, 0, 20, 16, 8) \
     X(256, 0, 16, 8, 30, 2, 0, 18, 16, 16) \
-    X(256, 1, 16, 16, 30, 2, 0, 17, 16, 16) \
-    X(256, 2, 16, 8, 30, 3, 0, 17, 16, 16) \
-    X(256, 3, 16, 8, 30, 2, 0, 146, 16, 16) \
     X(512, 0, 16, 8, 30, 2, 0, 17, 8, 8, 8) \
-    X(512, 1, 32, 16, 5, 1, 1, 17, 32, 16) \
-    X(512, 2, 16, 4, 30, 2, 0, 18, 8, 8, 8) \
-    X(512, 3, 32, 8, 5, 2, 1, 17, 32, 16) \
-    X(512, 4, 32, 16, 5, 1, 1, 145, 32, 16) \
-    X(512, 5, 16, 8, 30, 2, 0, 145, 8, 8, 8)
+    X(512, 1, 32, 16, 5, 1, 1, 17, 32, 16)
 
 #define B2F_ROT_TABLE_B(X) \
     X(1024, 0, 32, 8, 5, 1, 1, 17, 32, 32) \
-    X(1024, 1, 16, 8, 4, 1, 1, 17, 16, 8, 8) \
     X(1024, 2, 32, 8, 5, 1, 1, 145, 32, 32) \
     X(1024, 3, 32, 4, 5, 1, 1, 273, 32, 32) \
-    X(1024, 4, 32, 8, 5, 1, 1, 81, 32, 32) \
-    X(1024, 5, 32, 4, 5, 1, 1, 337, 32, 32) \
-    X(1024, 6, 16, 8, 4, 1, 1, 81, 16, 8, 8) \
     X(2048, 0, 16, 4, 4, 1, 1, 1, 16, 16, 8)
 
 #define B2F_ROT_TABLE(X) B2F_ROT_TABLE_A(X) B2F_ROT_TABLE_B(X)

@@ -693,9 +693,10 @@ def test_flag_barrier_kernel_index_logic(B, p):
 
 @pytest.mark.parametrize('shape,axis,dtype', [((96, 40, 24), 0, 'D'), ((20, 96, 24), 1, 'D'), ((20, 30, 96), 2, 'D'),
                                                ((20, 30, 96), 2, 'd'), ((40, 96, 6), 1, 'F'), ((12, 20, 192), 2, 'f'),
-                                               ((384, 10, 8), 0, 'D'), ((6, 10, 128), 2, 'd'), ((24, 95, 8), 1, 'D')])
+                                               ((384, 10, 8), 0, 'D'), ((6, 10, 128), 2, 'd'), ((24, 95, 8), 1, 'D'),
+                                               ((128, 6, 10), 0, 'D'), ((6, 160, 10), 1, 'F'), ((4, 6, 1024), 2, 'D')])
 def test_dealiasing_folded_into_the_transform(B, shape, axis, dtype, monkeypatch):
-    """3/2-rule padded stages (lengths 3 * 2^k) run as ONE kernel: the forward transform's last pass
+    """padded stages at any single-tile Stockham length (3 * 2^k for the 3/2 rule) run as ONE kernel: the forward transform's last pass
     writes only the kept modes, the backward transform's first pass reads them
     (b2f_plan_set_truncation) -- same values as the reference rule (libfft.py:263-311, restated in
     oracle/pfft_oracle.py and pinned on the reference's fixtures) and as the two-pass form."""
@@ -711,7 +712,13 @@ def test_dealiasing_folded_into_the_transform(B, shape, axis, dtype, monkeypatch
     got = np.asarray(f.forward(u)).copy()
     launches = _lib.launch_count() - n0
     n = shape[axis]
-    stockham = (n % 3 == 0 and (n // 3) & (n // 3 - 1) == 0) or (dtype in 'df' and n % 2 == 0 and (n // 2) & (n // 2 - 1) == 0)
+    def has_kernel(m, families):      # 2^k, 3 * 2^k, 5 * 2^k, 7 * 2^k
+        for f in families:
+            if m % f == 0 and m // f >= 1 and (m // f) & (m // f - 1) == 0 and (f == 1 and m >= 2 or f > 1):
+                return True
+        return False
+    # real transforms: every Stockham length of n / 2; c2c: the 2^k and 3 * 2^k families
+    stockham = has_kernel(n // 2, (1, 3, 5, 7)) if (dtype in 'df' and n % 2 == 0) else has_kernel(n, (1, 3))
     fused = bool(f.forward._fused_plan())
     assert fused == stockham, (shape, axis, dtype)
     if fused:
