@@ -24,6 +24,11 @@
 // One read and one write of the block per axis, as before; what changes is that
 // every request is either large or page-local.  Replaces fftw_execute_dft of a
 // multi-axis plan (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:52-56).
+//
+// Status: OPT-IN (option "rotate" / B2F_ROTATE=1).  Measured on 1024^3 complex128 each step runs at
+// 0.86 of the HBM roofline whatever the layout, which ties with the per-axis schedule (1.03 + 0.92 +
+// 0.69) in short runs and loses to it under the power cap (profiles/r2_rot_sweeps.txt, DESIGN.md
+// section 3).  The kernel also serves the transposing transform of the four-step split (lengths.h).
 #pragma once
 #include "fft_tma.cuh"
 
@@ -47,10 +52,9 @@ struct RotParams {
     int swap;
 };
 
-// padding of a pencil row in the stage (row pitch N + PAD elements, a multiple of 16 bytes):
-// a shared-memory wavefront serves 128 bytes, i.e. G = 128 / sizeof(element) lanes with
-// p = lane % P fastest and q consecutive; their addresses p * PITCH + q fall into G
-// different 16-byte... (element sized) slots when PITCH = G / P (mod G) for P <= G.
+// padding of a pencil row in the stage (row pitch N + PAD elements, a multiple of 16 bytes): a
+// shared-memory wavefront serves 128 bytes, i.e. G = 128 / sizeof(element) lanes, p = lane % P fastest
+// and q consecutive; their addresses p * PITCH + q are conflict free when PITCH = G / P (mod G), P <= G.
 template <class T, int P> struct RotPad {
     static constexpr int G = (int)(128 / (2 * sizeof(T)));
     static constexpr int unit = (int)(16 / (2 * sizeof(T)));       // elements per 16 bytes
