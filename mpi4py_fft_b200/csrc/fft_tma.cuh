@@ -355,7 +355,10 @@ __device__ __forceinline__ void fft_tma_body(const CUtensorMap* map_in, const Tm
         }
         load_stage<TF>(v, p, q, stages + (size_t)s * N * P, SWAP);
         if (TSTORE && tid == 0) bulk_wait_read();   // the previous tile's TMA stores have read the exchange buffer
-        __syncthreads();   // every thread has read stage s (and finished with the exchange buffer of the previous tile)
+        // TMA loader: one thread refills the stage for everybody, so everybody must have read it.  cp.async
+        // loader: a thread refills exactly the elements it has just read itself, and the barrier after
+        // wait_group above already separates the previous tile's exchange reads from this tile's writes.
+        if (LOADER == 0 || TSTORE) __syncthreads();
         const long long tn = t + (long long)STAGES * step;
         if (LOADER == 0) {
             if (tid == 0 && tn < prm.ntiles) issue(tn, s);
