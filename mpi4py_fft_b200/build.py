@@ -35,7 +35,15 @@ def _nvcc():
 
 
 def _sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+    """longest first (the mixed-radix and real-transform units take minutes, most others seconds):
+    with a fixed number of workers the build then ends when the work does, not when a late big unit does"""
+    def weight(name):
+        for key, w in (('real_mixed', 9), ('pow2_mixed', 8), ('fft_real', 6), ('cpa_c', 4), ('cpa_b', 4), ('tma_b', 3),
+                       ('pow2_large', 3), ('pow2_mid', 3), ('pow2_small', 3), ('rot', 2), ('chirpz', 2)):
+            if key in name:
+                return -w
+        return 0
+    return sorted((f for f in os.listdir(CSRC) if f.endswith('.cu')), key=lambda f: (weight(f), f))
 
 
 def _digest():

@@ -99,45 +99,53 @@
 // must divide E).  What FFTW plans for any N through its codelets
 // (/root/reference/mpi4py_fft/fftw/fftw_planxfftn.c:49-76) these lengths get as Stockham kernels
 // instead of the chirp-z detour.
-#define B2F_CONTIG_MIXED57(X)             \
-    X(5, 0, 5, 128, 30, 1, 5)             \
-    X(10, 0, 10, 64, 30, 1, 10)           \
-    X(20, 0, 20, 64, 30, 1, 20)           \
-    X(40, 0, 20, 32, 3, 1, 20, 2)         \
-    X(80, 0, 20, 32, 3, 1, 20, 4)         \
-    X(160, 0, 20, 16, 3, 1, 20, 4, 2)     \
-    X(320, 0, 20, 8, 3, 1, 20, 4, 4)      \
-    X(640, 0, 20, 4, 3, 1, 20, 4, 4, 2)   \
-    X(1280, 0, 20, 2, 3, 1, 20, 4, 4, 4)  \
-    X(7, 0, 7, 128, 30, 1, 7)             \
-    X(14, 0, 14, 64, 30, 1, 14)           \
-    X(28, 0, 28, 32, 30, 1, 28)           \
-    X(56, 0, 28, 32, 3, 1, 28, 2)         \
-    X(112, 0, 28, 32, 3, 1, 28, 4)        \
-    X(224, 0, 28, 16, 3, 1, 28, 4, 2)     \
-    X(448, 0, 28, 8, 3, 1, 28, 4, 4)      \
-    X(896, 0, 28, 4, 3, 1, 28, 4, 4, 2)   \
+#define B2F_CONTIG_MIXED5(X) \
+    X(5, 0, 5, 128, 30, 1, 5) \
+    X(10, 0, 10, 64, 30, 1, 10) \
+    X(20, 0, 20, 64, 30, 1, 20) \
+    X(40, 0, 20, 32, 3, 1, 20, 2) \
+    X(80, 0, 20, 32, 3, 1, 20, 4) \
+    X(160, 0, 20, 16, 3, 1, 20, 4, 2) \
+    X(320, 0, 20, 8, 3, 1, 20, 4, 4) \
+    X(640, 0, 20, 4, 3, 1, 20, 4, 4, 2) \
+    X(1280, 0, 20, 2, 3, 1, 20, 4, 4, 4)
+
+#define B2F_CONTIG_MIXED7(X) \
+    X(7, 0, 7, 128, 30, 1, 7) \
+    X(14, 0, 14, 64, 30, 1, 14) \
+    X(28, 0, 28, 32, 30, 1, 28) \
+    X(56, 0, 28, 32, 3, 1, 28, 2) \
+    X(112, 0, 28, 32, 3, 1, 28, 4) \
+    X(224, 0, 28, 16, 3, 1, 28, 4, 2) \
+    X(448, 0, 28, 8, 3, 1, 28, 4, 4) \
+    X(896, 0, 28, 4, 3, 1, 28, 4, 4, 2) \
     X(1792, 0, 28, 2, 3, 1, 28, 4, 4, 4)
 
-#define B2F_STRIDED_MIXED57(X)            \
-    X(5, 0, 5, 128, 30, 1, 5)             \
-    X(10, 0, 10, 64, 30, 1, 10)           \
-    X(20, 0, 20, 64, 30, 1, 20)           \
-    X(40, 0, 20, 32, 30, 1, 20, 2)        \
-    X(80, 0, 20, 32, 30, 1, 20, 4)        \
-    X(160, 0, 20, 16, 30, 1, 20, 4, 2)    \
-    X(320, 0, 20, 8, 30, 1, 20, 4, 4)     \
-    X(640, 0, 20, 8, 30, 1, 20, 4, 4, 2)  \
-    X(1280, 0, 20, 8, 30, 1, 20, 4, 4, 4) \
-    X(7, 0, 7, 128, 30, 1, 7)             \
-    X(14, 0, 14, 64, 30, 1, 14)           \
-    X(28, 0, 28, 32, 30, 1, 28)           \
-    X(56, 0, 28, 32, 30, 1, 28, 2)        \
-    X(112, 0, 28, 32, 30, 1, 28, 4)       \
-    X(224, 0, 28, 16, 30, 1, 28, 4, 2)    \
-    X(448, 0, 28, 8, 30, 1, 28, 4, 4)     \
-    X(896, 0, 28, 8, 30, 1, 28, 4, 4, 2)  \
+#define B2F_CONTIG_MIXED57(X) B2F_CONTIG_MIXED5(X) B2F_CONTIG_MIXED7(X)
+
+#define B2F_STRIDED_MIXED5(X) \
+    X(5, 0, 5, 128, 30, 1, 5) \
+    X(10, 0, 10, 64, 30, 1, 10) \
+    X(20, 0, 20, 64, 30, 1, 20) \
+    X(40, 0, 20, 32, 30, 1, 20, 2) \
+    X(80, 0, 20, 32, 30, 1, 20, 4) \
+    X(160, 0, 20, 16, 30, 1, 20, 4, 2) \
+    X(320, 0, 20, 8, 30, 1, 20, 4, 4) \
+    X(640, 0, 20, 8, 30, 1, 20, 4, 4, 2) \
+    X(1280, 0, 20, 8, 30, 1, 20, 4, 4, 4)
+
+#define B2F_STRIDED_MIXED7(X) \
+    X(7, 0, 7, 128, 30, 1, 7) \
+    X(14, 0, 14, 64, 30, 1, 14) \
+    X(28, 0, 28, 32, 30, 1, 28) \
+    X(56, 0, 28, 32, 30, 1, 28, 2) \
+    X(112, 0, 28, 32, 30, 1, 28, 4) \
+    X(224, 0, 28, 16, 30, 1, 28, 4, 2) \
+    X(448, 0, 28, 8, 30, 1, 28, 4, 4) \
+    X(896, 0, 28, 8, 30, 1, 28, 4, 4, 2) \
     X(1792, 0, 28, 4, 30, 1, 28, 4, 4, 4)
+
+#define B2F_STRIDED_MIXED57(X) B2F_STRIDED_MIXED5(X) B2F_STRIDED_MIXED7(X)
 
 // TMA-staged strided kernels (fft_tma.cuh):
 //   X(N, VAR, E, P, PS, STAGES, SPLIT, MINB, radices...)
@@ -270,45 +278,53 @@
     X(6144, 24, 2, 30, 1, 24, 8, 8, 4)
 
 // real transforms of length 2N, N = 5 * 2^k or 7 * 2^k (rows of B2F_*_MIXED57 without the VAR column)
-#define B2F_REAL_CONTIG_MIXED57(X)       \
-    X(5, 5, 128, 30, 1, 5)               \
-    X(10, 10, 64, 30, 1, 10)             \
-    X(20, 20, 64, 30, 1, 20)             \
-    X(40, 20, 32, 3, 1, 20, 2)           \
-    X(80, 20, 32, 3, 1, 20, 4)           \
-    X(160, 20, 16, 3, 1, 20, 4, 2)       \
-    X(320, 20, 8, 3, 1, 20, 4, 4)        \
-    X(640, 20, 4, 3, 1, 20, 4, 4, 2)     \
-    X(1280, 20, 2, 3, 1, 20, 4, 4, 4)    \
-    X(7, 7, 128, 30, 1, 7)               \
-    X(14, 14, 64, 30, 1, 14)             \
-    X(28, 28, 32, 30, 1, 28)             \
-    X(56, 28, 32, 3, 1, 28, 2)           \
-    X(112, 28, 32, 3, 1, 28, 4)          \
-    X(224, 28, 16, 3, 1, 28, 4, 2)       \
-    X(448, 28, 8, 3, 1, 28, 4, 4)        \
-    X(896, 28, 4, 3, 1, 28, 4, 4, 2)     \
+#define B2F_REAL_CONTIG_MIXED5(X) \
+    X(5, 5, 128, 30, 1, 5) \
+    X(10, 10, 64, 30, 1, 10) \
+    X(20, 20, 64, 30, 1, 20) \
+    X(40, 20, 32, 3, 1, 20, 2) \
+    X(80, 20, 32, 3, 1, 20, 4) \
+    X(160, 20, 16, 3, 1, 20, 4, 2) \
+    X(320, 20, 8, 3, 1, 20, 4, 4) \
+    X(640, 20, 4, 3, 1, 20, 4, 4, 2) \
+    X(1280, 20, 2, 3, 1, 20, 4, 4, 4)
+
+#define B2F_REAL_CONTIG_MIXED7(X) \
+    X(7, 7, 128, 30, 1, 7) \
+    X(14, 14, 64, 30, 1, 14) \
+    X(28, 28, 32, 30, 1, 28) \
+    X(56, 28, 32, 3, 1, 28, 2) \
+    X(112, 28, 32, 3, 1, 28, 4) \
+    X(224, 28, 16, 3, 1, 28, 4, 2) \
+    X(448, 28, 8, 3, 1, 28, 4, 4) \
+    X(896, 28, 4, 3, 1, 28, 4, 4, 2) \
     X(1792, 28, 2, 3, 1, 28, 4, 4, 4)
 
-#define B2F_REAL_STRIDED_MIXED57(X)      \
-    X(5, 5, 128, 30, 1, 5)               \
-    X(10, 10, 64, 30, 1, 10)             \
-    X(20, 20, 64, 30, 1, 20)             \
-    X(40, 20, 32, 30, 1, 20, 2)          \
-    X(80, 20, 32, 30, 1, 20, 4)          \
-    X(160, 20, 16, 30, 1, 20, 4, 2)      \
-    X(320, 20, 8, 30, 1, 20, 4, 4)       \
-    X(640, 20, 8, 30, 1, 20, 4, 4, 2)    \
-    X(1280, 20, 4, 30, 1, 20, 4, 4, 4)   \
-    X(7, 7, 128, 30, 1, 7)               \
-    X(14, 14, 64, 30, 1, 14)             \
-    X(28, 28, 32, 30, 1, 28)             \
-    X(56, 28, 32, 30, 1, 28, 2)          \
-    X(112, 28, 32, 30, 1, 28, 4)         \
-    X(224, 28, 16, 30, 1, 28, 4, 2)      \
-    X(448, 28, 8, 30, 1, 28, 4, 4)       \
-    X(896, 28, 8, 30, 1, 28, 4, 4, 2)    \
+#define B2F_REAL_CONTIG_MIXED57(X) B2F_REAL_CONTIG_MIXED5(X) B2F_REAL_CONTIG_MIXED7(X)
+
+#define B2F_REAL_STRIDED_MIXED5(X) \
+    X(5, 5, 128, 30, 1, 5) \
+    X(10, 10, 64, 30, 1, 10) \
+    X(20, 20, 64, 30, 1, 20) \
+    X(40, 20, 32, 30, 1, 20, 2) \
+    X(80, 20, 32, 30, 1, 20, 4) \
+    X(160, 20, 16, 30, 1, 20, 4, 2) \
+    X(320, 20, 8, 30, 1, 20, 4, 4) \
+    X(640, 20, 8, 30, 1, 20, 4, 4, 2) \
+    X(1280, 20, 4, 30, 1, 20, 4, 4, 4)
+
+#define B2F_REAL_STRIDED_MIXED7(X) \
+    X(7, 7, 128, 30, 1, 7) \
+    X(14, 14, 64, 30, 1, 14) \
+    X(28, 28, 32, 30, 1, 28) \
+    X(56, 28, 32, 30, 1, 28, 2) \
+    X(112, 28, 32, 30, 1, 28, 4) \
+    X(224, 28, 16, 30, 1, 28, 4, 2) \
+    X(448, 28, 8, 30, 1, 28, 4, 4) \
+    X(896, 28, 8, 30, 1, 28, 4, 4, 2) \
     X(1792, 28, 4, 30, 1, 28, 4, 4, 4)
+
+#define B2F_REAL_STRIDED_MIXED57(X) B2F_REAL_STRIDED_MIXED5(X) B2F_REAL_STRIDED_MIXED7(X)
 
 #define B2F_REAL_CONTIG(X) B2F_REAL_CONTIG_POW2(X) B2F_REAL_CONTIG_MIXED(X) B2F_REAL_CONTIG_MIXED57(X)
 #define B2F_REAL_STRIDED(X) B2F_REAL_STRIDED_POW2(X) B2F_REAL_STRIDED_MIXED(X) B2F_REAL_STRIDED_MIXED57(X)

@@ -2,12 +2,14 @@
 #include "fft_pow2_inst.cuh"
 namespace b2f {
 cudaError_t launch_real_mixed_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
-cudaError_t launch_real_mixed57_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_real_mixed5_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_real_mixed7_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 // n = complex length N (real length 2N); mode 1 = r2c, 2 = c2r
 cudaError_t launch_real_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st) {
     using T = double;
     if (n % 3 == 0) return launch_real_mixed_f64(n, mode, strided, prm, outer, st);
-    if (n % 5 == 0 || n % 7 == 0) return launch_real_mixed57_f64(n, mode, strided, prm, outer, st);
+    if (n % 5 == 0) return launch_real_mixed5_f64(n, mode, strided, prm, outer, st);
+    if (n % 7 == 0) return launch_real_mixed7_f64(n, mode, strided, prm, outer, st);
     if (strided) {
         B2F_REAL_STRIDED_POW2(B2F_INST_REAL_STRIDED)
     } else {

@@ -25,8 +25,16 @@ cudaError_t launch_pow2_mid_f32  (int n, int var, bool strided, const FftParams&
 cudaError_t launch_pow2_large_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_pow2_mixed_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
 cudaError_t launch_pow2_mixed_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
-cudaError_t launch_pow2_mixed57_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
-cudaError_t launch_pow2_mixed57_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed5_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed5_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed7_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+cudaError_t launch_pow2_mixed7_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
+inline cudaError_t launch_pow2_mixed57_f64(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st) {
+    return n % 5 == 0 ? launch_pow2_mixed5_f64(n, var, strided, prm, outer, st) : launch_pow2_mixed7_f64(n, var, strided, prm, outer, st);
+}
+inline cudaError_t launch_pow2_mixed57_f32(int n, int var, bool strided, const FftParams& prm, long long outer, cudaStream_t st) {
+    return n % 5 == 0 ? launch_pow2_mixed5_f32(n, var, strided, prm, outer, st) : launch_pow2_mixed7_f32(n, var, strided, prm, outer, st);
+}
 
 // real transforms of even length 2n through the n-point schedule (fft_real_*.cu); mode 1 = r2c, 2 = c2r
 cudaError_t launch_real_f64(int n, int mode, bool strided, const FftParams& prm, long long outer, cudaStream_t st);
