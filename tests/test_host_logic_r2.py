@@ -76,3 +76,52 @@ def test_bench_plane_waves_have_the_claimed_spectrum(shape, real):
     uh2 = torch.from_numpy(np.ascontiguousarray(spec_np))
     uh2[(0,) * len(shape)] += 1e-6
     assert bench.spectrum_error(torch, uh2, out_slices, ks, amps, real) > 5e-7
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location('b2f_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    return bench
+
+
+class _Args(object):
+    def __init__(self, config='c3', size=0, shape=''):
+        self.config, self.size, self.shape = config, size, shape
+
+
+def test_bench_workloads_are_the_baseline_configurations():
+    """BASELINE.json configs: c2 512^3 c128, c3 1024^3 c128 (headline), c4 2048^3 f32 r2c slab, c5 256^4 c128 grid (4, 2)"""
+    bench = _bench()
+    name, shape, dtype, kw = bench.workload(_Args('c3'), 8)
+    assert shape == (1024, 1024, 1024) and dtype == 'D' and kw == {} and '1024^3 complex128' in name
+    assert bench.workload(_Args('c2'), 1)[1] == (512, 512, 512)
+    name, shape, dtype, kw = bench.workload(_Args('c4'), 8)
+    assert shape == (2048, 2048, 2048) and dtype == 'f' and kw == dict(grid=(8,)) and 'slab' in name
+    name, shape, dtype, kw = bench.workload(_Args('c5'), 8)
+    assert shape == (256,) * 4 and dtype == 'D' and tuple(kw['grid']) == (4, 2)
+    assert tuple(bench.workload(_Args('c5'), 4)[3]['grid']) == (2, 2)
+    # the CPU arm keeps the decomposition KIND on its thread-ranks
+    assert bench.reference_kwargs(_Args('c4'), 16) == dict(grid=(16,))
+    assert bench.reference_kwargs(_Args('c5'), 16) == dict(grid=(4, 4))
+    assert bench.reference_kwargs(_Args('c3'), 16) == {}
+    assert bench.metric_name(_Args('c3')) == bench.metric_name(_Args('c2')) == "3D c2c fp64 forward+backward throughput"
+    # a reduced shape is labelled as such
+    a = _Args('c5', shape='64,64,64,64')
+    name, shape, dtype, kw = bench.workload_with_overrides(a, 2)
+    assert shape == (64, 64, 64, 64) and 'REDUCED' in name
+
+
+def test_reference_sample_shrinks_only_when_the_host_cannot_hold_the_workload(monkeypatch):
+    bench = _bench()
+    import psutil
+
+    class VM(object):
+        def __init__(self, avail):
+            self.available = avail
+    monkeypatch.setattr(psutil, 'virtual_memory', lambda: VM(200 * 2 ** 30))
+    assert bench.reference_shape((1024,) * 3, 'D') == (1024,) * 3          # 8.5 x 16 GiB fits in 200 GiB
+    monkeypatch.setattr(psutil, 'virtual_memory', lambda: VM(60 * 2 ** 30))
+    assert bench.reference_shape((1024,) * 3, 'D') == (512,) * 3
+    monkeypatch.setattr(psutil, 'virtual_memory', lambda: VM(8 * 2 ** 30))
+    assert bench.reference_shape((1024,) * 3, 'D') == (256,) * 3
