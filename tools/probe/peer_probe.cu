@@ -124,6 +124,19 @@ int main(int argc, char** argv) {
     }
     cudaStream_t st;
     CK(cudaStreamCreate(&st));
+    if (argc > 1 && ndev > 1) {
+        // "./peer_probe.bin ncu": one launch of each store pattern at 148 CTAs into the peer, for
+        // ncu --metrics nvltx__bytes.sum,nvltx__bytes_data_user.sum,nvltx__bytes_data_protocol.sum,gpu__time_duration.sum
+        CK(cudaFuncSetAttribute(bulk_kernel<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32768));
+        lsu_kernel<0><<<148, 256, 0, st>>>((const uint4*)src, (uint4*)dst_peer, bytes / 16);
+        lsu_kernel<8><<<148, 256, 0, st>>>((const uint4*)src, (uint4*)dst_peer, bytes / 16);
+        lsu_kernel<16><<<148, 256, 0, st>>>((const uint4*)src, (uint4*)dst_peer, bytes / 16);
+        bulk_kernel<32768><<<148, 128, 2 * 32768, st>>>(src, dst_peer, bytes);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        printf("ncu mode: 4 launches done\n");
+        return 0;
+    }
     const int grids[] = {8, 16, 32, 64, 96, 148, 296};
     for (int target = 0; target < (ndev > 1 ? 2 : 1); ++target) {
         char* dst = target ? dst_peer : dst_local;
